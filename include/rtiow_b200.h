@@ -1,0 +1,223 @@
+/* rtiow_b200.h — C ABI of the B200 render path for cbiffle/rtiow-rust.
+ *
+ * This is the drop-in boundary for ONE path of the reference crate:
+ *     par_cast / cast  ->  Camera::get_ray -> color -> World::hit_top -> Object::hit
+ *                      ->  Material::scatter / emitted -> Texture -> perlin
+ * (reference: src/lib.rs:363-397).  Everything below that call runs on the device in one
+ * sm_100a megakernel; nothing here falls back to the CPU.
+ *
+ * The reference has no FFI today (#![forbid(unsafe_code)], src/lib.rs:1): the seam is the Rust
+ * signature
+ *     pub fn par_cast(nx: usize, ny: usize, ns: usize, camera: &Camera, world: impl World) -> Image
+ * and this header is what a `rtiow-b200-sys` crate binds (INTEGRATION.md shows the Rust side).
+ * The host language flattens its scene (Box<dyn Object> tree, Bvh, Material, Texture) into the
+ * plain arrays of rtiow_scene_desc_t and hands over its Camera field for field.
+ *
+ * Conventions: plain pointers and sizes only; all input buffers are caller-owned HOST memory and
+ * are copied during the call; every function returns 0 on success or an RTIOW_ERR_* code and
+ * leaves a message readable with rtiow_b200_last_error() (thread-local).  A scene handle may be
+ * used from one host thread at a time.
+ */
+#ifndef RTIOW_B200_H
+#define RTIOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTIOW_B200_ABI_VERSION 1u
+
+enum {
+    RTIOW_OK = 0,
+    RTIOW_ERR_INVALID_ARG = 1,  /* null pointer, zero size, low >= high exposure ...             */
+    RTIOW_ERR_INVALID_SCENE = 2,/* index out of range, backward skip link, missing END ...       */
+    RTIOW_ERR_UNSUPPORTED = 3,  /* a nesting the flattened format cannot express                 */
+    RTIOW_ERR_CUDA = 4,         /* any CUDA runtime failure (message carries cudaGetErrorString) */
+    RTIOW_ERR_NO_DEVICE = 5     /* no sm_100 device: there is deliberately no CPU fallback       */
+};
+
+/* ---------------------------------------------------------------------------------------------
+ * Traversal stream.  The object tree is stored as ONE array of 32-byte items in the reference's
+ * own depth-first, left-first visiting order (Bvh::hit src/bvh.rs:85-120, And::hit
+ * src/object.rs:396-410, the list loop src/lib.rs:40-45 all visit children in order with a
+ * shrinking t_range.end, keeping the last accepted hit).  A box test that fails jumps to `skip`;
+ * everything else advances by one item, so traversal needs no stack and cannot loop.
+ *
+ * word a_w = kind | (payload << 4)            word b_w = material | (flags << 24)
+ * ------------------------------------------------------------------------------------------- */
+enum {
+    RTIOW_ITEM_END = 0,       /* end of stream (must be the last item)                               */
+    RTIOW_ITEM_BBOX = 1,      /* Bvh node box (src/aabb.rs:18-29): a=min b=max payload=skip index    */
+    RTIOW_ITEM_SPHERE = 2,    /* src/object.rs:82-111: a[0]=radius, b=inline Translate offset,
+                                 payload=frame                                                         */
+    RTIOW_ITEM_RECT = 3,      /* src/object.rs:183-218: a={k,range0.start,range0.end}
+                                 b={range1.start,range1.end,-} payload=frame                           */
+    RTIOW_ITEM_MEDIUM = 4,    /* src/object.rs:543-575: a[0]=density, a[1]=bits(medium id),
+                                 payload=frame of the medium; the NEXT item is its boundary primitive
+                                 (not visited on its own)                                              */
+    RTIOW_ITEM_SET_FRAME = 5  /* following BBOX items live in frame `payload`                          */
+};
+enum {
+    RTIOW_FLAG_HAS_OFFSET = 1u, /* SPHERE: innermost Translate folded into b[0..2] (object.rs:267-283) */
+    RTIOW_FLAG_FLIP = 2u,       /* innermost FlipNormals folded in (object.rs:241-253)                 */
+    RTIOW_FLAG_AXIS_SHIFT = 2u, /* RECT: (flags >> 2) & 3 = orthogonal axis 0=X 1=Y 2=Z                */
+};
+typedef struct rtiow_item_t {
+    float a[3];
+    uint32_t a_w;
+    float b[3];
+    uint32_t b_w;
+} rtiow_item_t;
+
+/* A frame is the chain of ray-transforming wrappers between the world and an item, applied
+ * outermost first to the ray and innermost first to the hit record, exactly as the nested
+ * Object::hit calls do.  Frame 0 is the world (no ops). */
+enum {
+    RTIOW_OP_TRANSLATE = 0,   /* v = offset            src/object.rs:267-283 */
+    RTIOW_OP_SCALE = 1,       /* v = factor            src/object.rs:301-319 */
+    RTIOW_OP_ROTATE_Y = 2,    /* v = {sin, cos, -}     src/object.rs:341-370 */
+    RTIOW_OP_LINEAR_MOVE = 3, /* v = motion per time   src/object.rs:496-512 */
+    RTIOW_OP_FLIP = 4         /* FlipNormals           src/object.rs:241-253 */
+};
+typedef struct rtiow_xform_op_t {
+    uint32_t kind;
+    float v[3];
+} rtiow_xform_op_t;
+typedef struct rtiow_frame_t {
+    uint32_t first_op;
+    uint32_t n_ops;
+} rtiow_frame_t;
+
+/* src/material.rs:11-40 */
+enum {
+    RTIOW_MAT_LAMBERTIAN = 0,    /* tex = albedo texture                    */
+    RTIOW_MAT_METAL = 1,         /* albedo[3], param = fuzz                 */
+    RTIOW_MAT_DIELECTRIC = 2,    /* param = ref_idx                         */
+    RTIOW_MAT_DIFFUSE_LIGHT = 3, /* tex = emission texture, param = brightness */
+    RTIOW_MAT_ISOTROPIC = 4      /* tex = albedo texture                    */
+};
+typedef struct rtiow_material_t {
+    uint32_t kind;
+    uint32_t tex;
+    float albedo[3];
+    float param;
+    uint32_t reserved[2];
+} rtiow_material_t;
+
+/* src/texture.rs:6-26 as data instead of closures */
+enum {
+    RTIOW_TEX_CONSTANT = 0, /* color                                  */
+    RTIOW_TEX_CHECKER = 1,  /* child0 (s >= 0) / child1 (s < 0)       */
+    RTIOW_TEX_PERLIN = 2    /* Vec3::from(turb(scale * p, 7))         */
+};
+typedef struct rtiow_texture_t {
+    uint32_t kind;
+    float color[3];
+    float scale;
+    uint32_t child0;
+    uint32_t child1;
+    uint32_t reserved;
+} rtiow_texture_t;
+
+/* What color() returns when a ray escapes.  BLACK is HEAD's behaviour (src/lib.rs:100);
+ * SKY_GRADIENT is the book-1 sky the README image was rendered with:
+ * strength * ((1-t)*c0 + t*c1), t = 0.5*(unit(dir).y + 1). */
+enum { RTIOW_BG_BLACK = 0, RTIOW_BG_SKY_GRADIENT = 1 };
+
+typedef struct rtiow_scene_desc_t {
+    uint32_t abi_version; /* RTIOW_B200_ABI_VERSION */
+    uint32_t n_items;
+    const rtiow_item_t* items;
+    uint32_t n_frames;
+    uint32_t n_ops;
+    const rtiow_frame_t* frames; /* frames[0] must be {0,0} */
+    const rtiow_xform_op_t* ops;
+    uint32_t n_materials;
+    uint32_t n_textures;
+    const rtiow_material_t* materials;
+    const rtiow_texture_t* textures;
+    const float* perlin_vecs;   /* 256*3 floats (src/perlin.rs:15-21); may be NULL if no Perlin texture */
+    const uint8_t* perlin_perm; /* 3*256 bytes: PERM_X, PERM_Y, PERM_Z (src/perlin.rs:5-13)             */
+    uint32_t background_kind;
+    float background_c0[3];
+    float background_c1[3];
+} rtiow_scene_desc_t;
+
+/* src/camera.rs:6-15, field for field (exposure: Range<f32> -> time0, time1). */
+typedef struct rtiow_camera_t {
+    float origin[3];
+    float lower_left_corner[3];
+    float horizontal[3];
+    float vertical[3];
+    float u[3];
+    float v[3];
+    float lens_radius;
+    float time0;
+    float time1;
+} rtiow_camera_t;
+
+typedef struct rtiow_stats_t {
+    double trace_ms;        /* device time of the path-tracing kernel(s) of the last render (CUDA events) */
+    double reduce_ms;       /* device time of the sample-fold kernel(s)                                   */
+    uint64_t samples;       /* pixel-samples traced by the last render                                   */
+    uint64_t segments;      /* hit_top calls (path segments) of the last render, counted on device        */
+    uint32_t kernel_launches; /* kernels launched by the last render                                      */
+    uint32_t passes;
+    uint32_t scene_in_smem; /* 1 if the scene blob was staged into shared memory                          */
+    uint32_t scene_bytes;
+    uint32_t grid, block, dyn_smem_bytes, regs_per_thread;
+} rtiow_stats_t;
+
+typedef struct rtiow_scene rtiow_scene_t;
+
+int rtiow_b200_abi_version(void);
+const char* rtiow_b200_last_error(void);
+
+/* Checks `desc` exactly as rtiow_b200_scene_create does, without touching a GPU. */
+int rtiow_b200_scene_validate(const rtiow_scene_desc_t* desc);
+
+/* Validates `desc`, copies it to `device` (CUDA ordinal) and returns a handle. */
+int rtiow_b200_scene_create(const rtiow_scene_desc_t* desc, int device, rtiow_scene_t** out);
+void rtiow_b200_scene_destroy(rtiow_scene_t* scene);
+
+/* par_cast (src/lib.rs:363-376) with an explicit seed: out_rgb receives ny*nx*3 floats, row 0 =
+ * TOP scanline (lib.rs:326-330), linear (pre-gamma), already divided by ns (lib.rs:374) — i.e.
+ * exactly `Image`.  Samples of a pixel are summed left to right from 0 in sample order
+ * (src/vec3.rs:195-203).  out_rgb is HOST memory. */
+int rtiow_b200_render(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny, uint32_t ns,
+                      uint64_t seed, float* out_rgb);
+
+/* Rows [row_begin, row_end) of the same image (row 0 = top): the unit of multi-GPU sharding.
+ * The result is bit-identical to the corresponding rows of rtiow_b200_render. */
+int rtiow_b200_render_rows(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny, uint32_t ns,
+                           uint64_t seed, uint32_t row_begin, uint32_t row_end, float* out_rows);
+
+/* Same, but `d_out_rows` is DEVICE memory on the scene's device and the work is only enqueued on
+ * `cuda_stream` (a cudaStream_t, NULL = default stream); nothing is synchronised. */
+int rtiow_b200_render_rows_device(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny,
+                                  uint32_t ns, uint64_t seed, uint32_t row_begin, uint32_t row_end,
+                                  float* d_out_rows, void* cuda_stream);
+
+/* Parity/debug: per-sample radiance before the fold, HOST memory,
+ * (row_end-row_begin)*nx*ns*4 floats laid out [row][x][sample]{r,g,b,segments}. */
+int rtiow_b200_render_samples(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny,
+                              uint32_t ns, uint64_t seed, uint32_t row_begin, uint32_t row_end, float* out_samples);
+
+/* print_ppm's per-channel sqrt + to_u8 (src/lib.rs:344-361) on the device: n floats -> n bytes. */
+int rtiow_b200_ppm_quantise(rtiow_scene_t* scene, const float* linear, size_t n, uint8_t* out);
+
+/* Synchronises the scene's device and reports the last render. */
+int rtiow_b200_get_stats(rtiow_scene_t* scene, rtiow_stats_t* out);
+
+/* Tuning knobs (0 = keep default): threads per CTA, CTAs per SM, staging budget in MiB,
+ * force_global != 0 keeps the scene in global memory even if it fits shared memory. */
+int rtiow_b200_set_tuning(rtiow_scene_t* scene, uint32_t cta_threads, uint32_t ctas_per_sm, uint32_t staging_mib,
+                          int force_global);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTIOW_B200_H */

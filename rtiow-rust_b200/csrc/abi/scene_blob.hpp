@@ -1,0 +1,169 @@
+// Scene descriptor validation and the device blob layout, as plain C++ (no CUDA): shared by the
+// C ABI implementation (rtiow_b200.cu) and by tests/kernel_host_harness.cpp.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../../include/rtiow_b200.h"
+
+namespace rtiow {
+
+inline bool ops_prefix(const rtiow_scene_desc_t* d, uint32_t outer, uint32_t inner) {
+    // true if frame `outer`'s op list is a prefix of frame `inner`'s
+    const rtiow_frame_t& fo = d->frames[outer];
+    const rtiow_frame_t& fi = d->frames[inner];
+    if (fo.n_ops > fi.n_ops) return false;
+    for (uint32_t k = 0; k < fo.n_ops; ++k)
+        if (std::memcmp(&d->ops[fo.first_op + k], &d->ops[fi.first_op + k], sizeof(rtiow_xform_op_t)) != 0) return false;
+    return true;
+}
+
+inline int validate_desc(const rtiow_scene_desc_t* d, bool* has_frames, bool* uses_perlin, std::string* msg) {
+    auto bad = [&](const std::string& m) { *msg = m; return static_cast<int>(RTIOW_ERR_INVALID_SCENE); };
+    auto badarg = [&](const std::string& m) { *msg = m; return static_cast<int>(RTIOW_ERR_INVALID_ARG); };
+    if (d->abi_version != RTIOW_B200_ABI_VERSION) return badarg("abi_version mismatch");
+    if (!d->items || d->n_items == 0) return bad("Can't render a scene with zero items");
+    if (d->n_items >= (1u << 28)) return bad("too many items");
+    if (!d->frames || d->n_frames == 0 || d->frames[0].n_ops != 0) return bad("frames[0] must be the world frame");
+    if (d->n_materials >= (1u << 24)) return bad("too many materials");
+    if ((d->n_ops && !d->ops) || (d->n_materials && !d->materials) || (d->n_textures && !d->textures))
+        return badarg("null array with non-zero count");
+    for (uint32_t f = 0; f < d->n_frames; ++f) {
+        const rtiow_frame_t& fr = d->frames[f];
+        if (static_cast<uint64_t>(fr.first_op) + fr.n_ops > d->n_ops) return bad("frame op range out of bounds");
+    }
+    for (uint32_t k = 0; k < d->n_ops; ++k)
+        if (d->ops[k].kind > RTIOW_OP_FLIP) return bad("unknown transform op");
+    *uses_perlin = false;
+    for (uint32_t t = 0; t < d->n_textures; ++t) {
+        const rtiow_texture_t& tx = d->textures[t];
+        if (tx.kind > RTIOW_TEX_PERLIN) return bad("unknown texture kind");
+        if (tx.kind == RTIOW_TEX_CHECKER && (tx.child0 >= t || tx.child1 >= t))
+            return bad("checker children must precede their parent (keeps the texture graph acyclic)");
+        if (tx.kind == RTIOW_TEX_PERLIN) *uses_perlin = true;
+    }
+    if (*uses_perlin && (!d->perlin_vecs || !d->perlin_perm)) return bad("Perlin texture without Perlin tables");
+    for (uint32_t m = 0; m < d->n_materials; ++m) {
+        const rtiow_material_t& mt = d->materials[m];
+        if (mt.kind > RTIOW_MAT_ISOTROPIC) return bad("unknown material kind");
+        const bool textured = mt.kind == RTIOW_MAT_LAMBERTIAN || mt.kind == RTIOW_MAT_DIFFUSE_LIGHT || mt.kind == RTIOW_MAT_ISOTROPIC;
+        if (textured && mt.tex >= d->n_textures) return bad("material texture index out of range");
+    }
+    if ((d->items[d->n_items - 1].a_w & 15u) != RTIOW_ITEM_END) return bad("item stream must end with RTIOW_ITEM_END");
+
+    *has_frames = false;
+    std::vector<uint32_t> frame_at(d->n_items);
+    std::vector<char> is_boundary(d->n_items, 0);
+    uint32_t cur = 0;
+    auto prim_ok = [&](uint32_t i, uint32_t outer_frame) -> const char* {
+        const rtiow_item_t& it = d->items[i];
+        const uint32_t kind = it.a_w & 15u, frame = it.a_w >> 4;
+        if (kind != RTIOW_ITEM_SPHERE && kind != RTIOW_ITEM_RECT) return "expected a primitive item";
+        if (frame >= d->n_frames) return "primitive frame out of range";
+        if ((it.b_w & 0x00ffffffu) >= d->n_materials) return "primitive material out of range";
+        if (!ops_prefix(d, outer_frame, frame)) return "primitive frame does not extend the enclosing frame";
+        if (kind == RTIOW_ITEM_RECT && (((it.b_w >> 24) >> 2) & 3u) > 2u) return "rect axis out of range";
+        return nullptr;
+    };
+    for (uint32_t i = 0; i < d->n_items; ++i) {
+        frame_at[i] = cur;
+        const rtiow_item_t& it = d->items[i];
+        const uint32_t kind = it.a_w & 15u, payload = it.a_w >> 4;
+        switch (kind) {
+            case RTIOW_ITEM_END:
+                if (i + 1 != d->n_items) return bad("RTIOW_ITEM_END before the end of the stream");
+                break;
+            case RTIOW_ITEM_BBOX:
+                if (payload <= i || payload >= d->n_items) return bad("BBOX skip link must point forward, inside the stream");
+                break;
+            case RTIOW_ITEM_SPHERE:
+            case RTIOW_ITEM_RECT:
+                if (const char* m = prim_ok(i, cur)) return bad(m);
+                break;
+            case RTIOW_ITEM_MEDIUM: {
+                if (payload >= d->n_frames || !ops_prefix(d, cur, payload)) return bad("medium frame invalid");
+                if ((it.b_w & 0x00ffffffu) >= d->n_materials) return bad("medium material out of range");
+                if (i + 2 >= d->n_items) return bad("medium without boundary item");
+                if (const char* m = prim_ok(i + 1, payload)) return bad(std::string("medium boundary: ") + m);
+                uint32_t mid;
+                std::memcpy(&mid, &it.a[1], 4);
+                if (mid >= 65536u - 16u) return bad("medium id too large");
+                frame_at[i + 1] = cur;
+                is_boundary[i + 1] = 1;
+                ++i;  // boundary item is consumed with the medium
+                break;
+            }
+            case RTIOW_ITEM_SET_FRAME:
+                if (payload >= d->n_frames) return bad("SET_FRAME frame out of range");
+                cur = payload;
+                *has_frames = true;
+                break;
+            default:
+                return bad("unknown item kind");
+        }
+    }
+    for (uint32_t i = 0; i < d->n_items; ++i) {
+        const rtiow_item_t& it = d->items[i];
+        if ((it.a_w & 15u) == RTIOW_ITEM_BBOX) {
+            const uint32_t tgt = it.a_w >> 4;
+            if (frame_at[tgt] != frame_at[i]) return bad("BBOX skip link crosses a frame change");
+            if (is_boundary[tgt]) return bad("BBOX skip link lands on a medium boundary item");
+        }
+    }
+    return RTIOW_OK;
+}
+
+
+struct BlobLayout {
+    uint32_t off_frames, off_ops, off_mats, off_tex, off_pvecs, off_pperm;
+};
+
+// items | frames | ops | materials | textures | perlin vecs (float4) | perlin perms; every section
+// starts on a 128-byte boundary so the whole blob can be moved with 128 B-granular TMA bulk copies.
+inline std::vector<unsigned char> build_blob(const rtiow_scene_desc_t* d, bool uses_perlin, BlobLayout* lay) {
+    std::vector<unsigned char> blob;
+    auto align_up = [](size_t v) { return (v + 127u) / 128u * 128u; };
+    auto append = [&](const void* src, size_t bytes) -> uint32_t {
+        const size_t off = align_up(blob.size());
+        blob.resize(off + bytes, 0);
+        if (bytes) std::memcpy(blob.data() + off, src, bytes);
+        return static_cast<uint32_t>(off);
+    };
+    append(d->items, sizeof(rtiow_item_t) * d->n_items);
+    lay->off_frames = append(d->frames, sizeof(rtiow_frame_t) * d->n_frames);
+    lay->off_ops = append(d->ops, sizeof(rtiow_xform_op_t) * d->n_ops);
+    {   // materials, with constant textures baked in: {kind | texkind<<8, tex, param, 0} {color/albedo, 0}
+        std::vector<float> mats(8 * static_cast<size_t>(d->n_materials), 0.f);
+        for (uint32_t m = 0; m < d->n_materials; ++m) {
+            const rtiow_material_t& mt = d->materials[m];
+            uint32_t texkind = 0xffu;
+            float col[3] = {mt.albedo[0], mt.albedo[1], mt.albedo[2]};
+            const bool textured = mt.kind == RTIOW_MAT_LAMBERTIAN || mt.kind == RTIOW_MAT_DIFFUSE_LIGHT || mt.kind == RTIOW_MAT_ISOTROPIC;
+            if (textured) {
+                texkind = d->textures[mt.tex].kind;
+                if (texkind == RTIOW_TEX_CONSTANT) std::memcpy(col, d->textures[mt.tex].color, 12);
+            }
+            const uint32_t w0 = mt.kind | (texkind << 8);
+            std::memcpy(&mats[8 * m + 0], &w0, 4);
+            std::memcpy(&mats[8 * m + 1], &mt.tex, 4);
+            mats[8 * m + 2] = mt.param;
+            mats[8 * m + 4] = col[0]; mats[8 * m + 5] = col[1]; mats[8 * m + 6] = col[2];
+        }
+        lay->off_mats = append(mats.data(), mats.size() * 4);
+    }
+    lay->off_tex = append(d->textures, sizeof(rtiow_texture_t) * d->n_textures);
+    if (uses_perlin) {
+        std::vector<float> v4(4 * 256, 0.f);
+        for (int i = 0; i < 256; ++i) std::memcpy(&v4[4 * i], d->perlin_vecs + 3 * i, 12);
+        lay->off_pvecs = append(v4.data(), v4.size() * 4);
+        lay->off_pperm = append(d->perlin_perm, 768);
+    } else {
+        lay->off_pvecs = lay->off_pperm = 0;
+    }
+    blob.resize(align_up(blob.size()), 0);
+    return blob;
+}
+
+}  // namespace rtiow

@@ -1,0 +1,438 @@
+// Per-path logic of the render megakernel: what ONE lane does for ONE pixel-sample.
+//   generate_camera_ray : lib.rs:366-370 + Camera::get_ray (camera.rs:52-63)
+//   hit_top_stream      : World::hit_top (lib.rs:33-55) over the flattened traversal stream
+//                         = Bvh::hit / Aabb::hit / And::hit / Object::hit in the reference's order
+//   shade_and_scatter   : the body of color()'s loop (lib.rs:73-98): emitted + Material::scatter
+// The functions are __host__ __device__ so that tests/kernel_host_harness.cpp can run exactly this
+// code on the CPU against the oracle (flattener and stream logic can then be debugged without a
+// GPU).  The shipped library only ever runs them inside render_kernel (render_kernel.cuh).
+#pragma once
+#include "rt_math.cuh"
+
+namespace rtiow {
+
+constexpr float kNear = 0.001f;               // lib.rs:35,53
+constexpr float kF32Max = 3.402823466e+38f;   // std::f32::MAX
+constexpr float kF32Min = -3.402823466e+38f;  // std::f32::MIN
+constexpr uint32_t kNoHit = 0xffffffffu;
+
+// item kinds / flags mirror include/rtiow_b200.h
+enum : uint32_t { IT_END = 0, IT_BBOX = 1, IT_SPHERE = 2, IT_RECT = 3, IT_MEDIUM = 4, IT_SET_FRAME = 5 };
+enum : uint32_t { FL_HAS_OFFSET = 1u, FL_FLIP = 2u };
+enum : uint32_t { OP_TRANSLATE = 0, OP_SCALE = 1, OP_ROTATE_Y = 2, OP_LINEAR_MOVE = 3, OP_FLIP = 4 };
+enum : uint32_t { MAT_LAMBERTIAN = 0, MAT_METAL = 1, MAT_DIELECTRIC = 2, MAT_DIFFUSE_LIGHT = 3, MAT_ISOTROPIC = 4 };
+enum : uint32_t { TEX_CONSTANT = 0, TEX_CHECKER = 1, TEX_PERLIN = 2 };
+
+struct KParams {
+    const unsigned char* blob;  // device scene blob; items start at offset 0
+    uint32_t blob_bytes;
+    uint32_t off_frames, off_ops, off_mats, off_tex, off_pvecs, off_pperm;
+    float cam[21];              // rtiow_camera_t
+    uint32_t nx, ny, row_begin, n_rows;
+    uint32_t s_begin, s_count;  // samples [s_begin, s_begin + s_count) of every pixel in this pass
+    uint32_t npix, n_groups;
+    uint32_t key0, key1;
+    uint32_t bg_kind;
+    float bg0[3], bg1[3];
+    float4* staging;            // [s_count][npix] {r, g, b, segments}
+    unsigned int* work_counter;
+};
+
+// Views into the scene blob (shared or global memory on the device).
+struct Scene {
+    const float4* items;
+    const uint2* frames;
+    const float4* ops;
+    const float4* mats;
+    const float4* tex;
+    const float4* pvecs;
+    const unsigned char* pperm;
+};
+
+RT_HD Scene scene_views(const unsigned char* base, const KParams& P) {
+    Scene sc;
+    sc.items = reinterpret_cast<const float4*>(base);
+    sc.frames = reinterpret_cast<const uint2*>(base + P.off_frames);
+    sc.ops = reinterpret_cast<const float4*>(base + P.off_ops);
+    sc.mats = reinterpret_cast<const float4*>(base + P.off_mats);
+    sc.tex = reinterpret_cast<const float4*>(base + P.off_tex);
+    sc.pvecs = reinterpret_cast<const float4*>(base + P.off_pvecs);
+    sc.pperm = base + P.off_pperm;
+    return sc;
+}
+
+struct Rng {
+    uint32_t k0, k1, pixel, sample;
+    RT_HD U4 block(uint32_t bounce, uint32_t purpose, uint32_t index) const {
+        return philox4x32_10(k0, k1, pixel, sample, (bounce << 16) | purpose, index);
+    }
+};
+
+// One pixel-sample in flight.
+struct PathState {
+    uint32_t pix, samp, bounce;
+    V3 ro, rd, strength;
+    float rtime;
+    Rng rng;
+};
+
+RT_HD void apply_op_ray(const float4 op, V3& o, V3& d, float time) {
+    const uint32_t kind = f2u(op.x);
+    const V3 v = mk(op.y, op.z, op.w);
+    if (kind == OP_TRANSLATE) {            // object.rs:275-278
+        o = o - v;
+    } else if (kind == OP_SCALE) {         // object.rs:309-313
+        o = o / v;
+        d = d / v;
+    } else if (kind == OP_ROTATE_Y) {      // object.rs:357-361
+        o = rot_y(o, -v.x, v.y);
+        d = rot_y(d, -v.x, v.y);
+    } else if (kind == OP_LINEAR_MOVE) {   // object.rs:505-508
+        o = o - time * v;
+    }
+}
+
+RT_HD void apply_op_hit(const float4 op, V3& p, V3& n) {
+    const uint32_t kind = f2u(op.x);
+    const V3 v = mk(op.y, op.z, op.w);
+    if (kind == OP_TRANSLATE) {            // object.rs:279-282
+        p = p + v;
+    } else if (kind == OP_SCALE) {         // object.rs:314-318
+        p = p * v;
+        n = n / v;
+    } else if (kind == OP_ROTATE_Y) {      // object.rs:365-369
+        p = rot_y(p, v.x, v.y);
+        n = rot_y(n, v.x, v.y);
+    } else if (kind == OP_FLIP) {          // object.rs:249-252
+        n = -n;
+    }                                      // LinearMove: result returned unmodified (object.rs:504-511)
+}
+
+// Sphere::hit (object.rs:82-111) on a ray already in the sphere's frame.
+RT_HD bool sphere_hit_t(V3 o, V3 d, float radius, float t_lo, float t_hi, float& t_out) {
+    const float a = dot(d, d);
+    const float b = dot(o, d);
+    const float c = dot(o, o) - radius * radius;
+    const float disc = b * b - a * c;
+    if (disc > 0.f) {
+        const float sq = sqrtf(disc);
+        float t = (-b - sq) / a;
+        if (t < t_hi && t >= t_lo) { t_out = t; return true; }
+        t = (-b + sq) / a;
+        if (t < t_hi && t >= t_lo) { t_out = t; return true; }
+    }
+    return false;
+}
+
+RT_HD float axis_of(V3 v, uint32_t axis) { return axis == 0 ? v.x : (axis == 1 ? v.y : v.z); }
+
+// Rect<A>::hit (object.rs:183-218); a = {k, r0.start, r0.end}, b = {r1.start, r1.end}
+RT_HD bool rect_hit_t(V3 o, V3 d, uint32_t axis, float4 ia, float4 ib, float t_lo, float t_hi, float& t_out) {
+    const uint32_t o1 = axis == 0 ? 1u : 0u, o2 = axis == 2 ? 1u : 2u;  // object.rs:153-181
+    const float t = (ia.x - axis_of(o, axis)) / axis_of(d, axis);
+    if (t < t_lo || t >= t_hi) return false;
+    const float x = axis_of(o, o1) + t * axis_of(d, o1);
+    const float y = axis_of(o, o2) + t * axis_of(d, o2);
+    if (x < ia.y || x >= ia.z || y < ib.x || y >= ib.y) return false;
+    t_out = t;
+    return true;
+}
+
+// Any primitive item against a ray in the frame just outside the item's own extra ops.
+// `skip_ops` = how many leading ops of the item's frame are already applied to (o, d).
+RT_HD bool prim_hit_t(const Scene& sc, float4 ia, float4 ib, V3 o, V3 d, float time, uint32_t skip_ops, float t_lo,
+                      float t_hi, float& t_out) {
+    const uint32_t kind = f2u(ia.w) & 15u;
+    const uint32_t frame = f2u(ia.w) >> 4;
+    const uint32_t flags = f2u(ib.w) >> 24;
+    const uint2 fr = sc.frames[frame];
+    for (uint32_t k = skip_ops; k < fr.y; ++k) apply_op_ray(sc.ops[fr.x + k], o, d, time);
+    if (kind == IT_SPHERE) {
+        if (flags & FL_HAS_OFFSET) o = o - mk(ib.x, ib.y, ib.z);
+        return sphere_hit_t(o, d, ia.x, t_lo, t_hi, t_out);
+    }
+    return rect_hit_t(o, d, (flags >> 2) & 3u, ia, ib, t_lo, t_hi, t_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Textures (texture.rs) and Perlin noise (perlin.rs)
+// ------------------------------------------------------------------------------------------------
+RT_HD_NOINLINE float perlin_noise(const Scene& sc, V3 p) {  // perlin.rs:49-64 + trilinear_interp :31-47
+    const V3 ijk = mk(floorf(p.x), floorf(p.y), floorf(p.z));
+    const V3 uvw = p - ijk;
+    const int bi = f2i_rz_sat(ijk.x), bj = f2i_rz_sat(ijk.y), bk = f2i_rz_sat(ijk.z);  // `as i32`
+    const V3 uvw3 = uvw * uvw * (splat(3.f) - 2.f * uvw);
+    const V3 uvw3_inv = splat(1.f) - uvw3;
+    float accum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint32_t ix = sc.pperm[(static_cast<uint32_t>(bi) + static_cast<uint32_t>(i)) & 255u];
+                const uint32_t iy = sc.pperm[256u + ((static_cast<uint32_t>(bj) + static_cast<uint32_t>(j)) & 255u)];
+                const uint32_t iz = sc.pperm[512u + ((static_cast<uint32_t>(bk) + static_cast<uint32_t>(k)) & 255u)];
+                const float4 cv = sc.pvecs[ix ^ iy ^ iz];
+                const V3 ijkf = mk(static_cast<float>(i), static_cast<float>(j), static_cast<float>(k));
+                const float weight = dot(mk(cv.x, cv.y, cv.z), uvw - ijkf);
+                const V3 m = ijkf * uvw3 + (splat(1.f) - ijkf) * uvw3_inv;
+                accum = accum + ((m.x * m.y) * m.z) * weight;
+            }
+    return accum;
+}
+
+RT_HD_NOINLINE float perlin_turb(const Scene& sc, V3 p) {  // perlin.rs:66-75 with depth 7 (texture.rs:24)
+    float accum = 0.f, weight = 1.f;
+    for (int i = 0; i < 7; ++i) {
+        accum += weight * perlin_noise(sc, p);
+        weight *= 0.5f;
+        p = 2.f * p;
+    }
+    return fabsf(accum);
+}
+
+RT_HD_NOINLINE V3 texture_eval(const Scene& sc, uint32_t id, V3 p) {
+    for (;;) {
+        const float4 t0 = sc.tex[2 * id];
+        const uint32_t kind = f2u(t0.x);
+        if (kind == TEX_CONSTANT) return mk(t0.y, t0.z, t0.w);            // texture.rs:8-10
+        const float4 t1 = sc.tex[2 * id + 1];
+        if (kind == TEX_PERLIN) return splat(perlin_turb(sc, t1.x * p));  // texture.rs:23-26
+        const V3 q = 10.f * p;                                            // checker, texture.rs:12-21
+        const float s = (sin_f32(q.x) * sin_f32(q.y)) * sin_f32(q.z);
+        id = s < 0.f ? f2u(t1.z) : f2u(t1.y);
+    }
+}
+
+// Material's texture at p; constant textures were baked into the material record at scene upload.
+RT_HD V3 material_texture(const Scene& sc, float4 m0, float4 m1, V3 p) {
+    const uint32_t texkind = (f2u(m0.x) >> 8) & 0xffu;
+    if (texkind == TEX_CONSTANT) return mk(m1.x, m1.y, m1.z);
+    return texture_eval(sc, f2u(m0.y), p);
+}
+
+RT_HD V3 in_unit_sphere(const Rng& rng, uint32_t bounce) {  // vec3.rs:19-26
+    for (uint32_t k = 0;; ++k) {
+        const U4 w = rng.block(bounce, PURPOSE_SCATTER, k);
+        const V3 v = 2.f * mk(unit_f32(w.x), unit_f32(w.y), unit_f32(w.z)) - splat(1.f);
+        if (dot(v, v) < 1.f) return v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// lib.rs:366-370 + Camera::get_ray (camera.rs:52-63) for sample st.samp of pixel st.pix
+// (pix counts row-major from the top-left of the rendered row block).
+// ------------------------------------------------------------------------------------------------
+RT_HD void generate_camera_ray(const KParams& P, PathState& st) {
+    const uint32_t r = st.pix / P.nx, x = st.pix - r * P.nx;
+    const uint32_t y = P.ny - 1u - (P.row_begin + r);  // (0..ny).rev()  lib.rs:326-330
+    st.rng.pixel = y * P.nx + x;
+    st.rng.sample = st.samp;
+    const U4 cw = st.rng.block(0u, PURPOSE_CAMERA, 0u);
+    const float s = (static_cast<float>(x) + unit_f32(cw.x)) / static_cast<float>(P.nx);  // lib.rs:368
+    const float t = (static_cast<float>(y) + unit_f32(cw.y)) / static_cast<float>(P.ny);  // lib.rs:369
+    V3 disc;
+    for (uint32_t k = 0;; ++k) {  // Vec3::in_unit_disc  vec3.rs:32-39
+        const U4 lw = st.rng.block(0u, PURPOSE_LENS, k >> 1);
+        const uint32_t wa = (k & 1u) ? lw.z : lw.x, wb = (k & 1u) ? lw.w : lw.y;
+        disc = 2.f * mk(unit_f32(wa), unit_f32(wb), 0.f) - mk(1.f, 1.f, 0.f);
+        if (dot(disc, disc) < 1.f) break;
+    }
+    const V3 lens = P.cam[18] * disc;
+    const V3 cu = mk(P.cam[12], P.cam[13], P.cam[14]), cv = mk(P.cam[15], P.cam[16], P.cam[17]);
+    const V3 offset = lens.x * cu + lens.y * cv;
+    // rng.gen_range(exposure.start, exposure.end): rand 0.6.5 UniformFloat::sample_single
+    const float scale = P.cam[20] - P.cam[19], toff = P.cam[19] - scale;
+    float time;
+    for (uint32_t k = 0;; ++k) {
+        uint32_t word;
+        if (k == 0) word = cw.z;
+        else if (k == 1) word = cw.w;
+        else {
+            const U4 tw = st.rng.block(0u, PURPOSE_CAMERA, 1u + ((k - 2u) >> 2));
+            const uint32_t sel = (k - 2u) & 3u;
+            word = sel == 0 ? tw.x : (sel == 1 ? tw.y : (sel == 2 ? tw.z : tw.w));
+        }
+        time = f32_1_2(word) * scale + toff;
+        if (time < P.cam[20]) break;
+    }
+    const V3 corigin = mk(P.cam[0], P.cam[1], P.cam[2]);
+    const V3 llc = mk(P.cam[3], P.cam[4], P.cam[5]);
+    const V3 hor = mk(P.cam[6], P.cam[7], P.cam[8]), ver = mk(P.cam[9], P.cam[10], P.cam[11]);
+    st.ro = corigin + offset;
+    st.rd = llc + s * hor + t * ver - corigin - offset;
+    st.rtime = time;
+    st.strength = splat(1.f);
+    st.bounce = 0u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// World::hit_top over the threaded stream, in the reference's visiting order.  Returns the index
+// of the winning item (kNoHit if none) and its t.
+// ------------------------------------------------------------------------------------------------
+template <bool kFrames>
+RT_HD uint32_t hit_top_stream(const Scene& sc, const PathState& st, float& best_t_out) {
+    float best_t = kF32Max;
+    uint32_t best = kNoHit;
+    V3 fo = st.ro, fd = st.rd;  // ray in the current BBOX frame
+    uint32_t f_nops = 0u;
+    V3 inv = mk(1.f / fd.x, 1.f / fd.y, 1.f / fd.z);  // aabb.rs:19 (same value at every node)
+    uint32_t i = 0u;
+    for (;;) {
+        const float4 ia = sc.items[2u * i];
+        const uint32_t kind = f2u(ia.w) & 15u;
+        if (kind == IT_BBOX) {  // Aabb::hit  aabb.rs:18-29
+            const float4 ib = sc.items[2u * i + 1u];
+            const float ax = (ia.x - fo.x) * inv.x, ay = (ia.y - fo.y) * inv.y, az = (ia.z - fo.z) * inv.z;
+            const float bx = (ib.x - fo.x) * inv.x, by = (ib.y - fo.y) * inv.y, bz = (ib.z - fo.z) * inv.z;
+            const float n0x = inv.x < 0.f ? bx : ax, n1x = inv.x < 0.f ? ax : bx;
+            const float n0y = inv.y < 0.f ? by : ay, n1y = inv.y < 0.f ? ay : by;
+            const float n0z = inv.z < 0.f ? bz : az, n1z = inv.z < 0.f ? az : bz;
+            const float start = rt_max(kNear, rt_max(rt_max(n0x, n0y), n0z));
+            const float end = rt_min(best_t, rt_min(rt_min(n1x, n1y), n1z));
+            i = (end > start) ? i + 1u : (f2u(ia.w) >> 4);
+        } else if (kind == IT_SPHERE || kind == IT_RECT) {
+            const float4 ib = sc.items[2u * i + 1u];
+            float t;
+            if (prim_hit_t(sc, ia, ib, fo, fd, st.rtime, f_nops, kNear, best_t, t)) {
+                best_t = t;  // nearest = rec.t (lib.rs:42) / t_range.end = h.t (bvh.rs:98-100, object.rs:404-406)
+                best = i;
+            }
+            i += 1u;
+        } else if (kind == IT_MEDIUM) {  // ConstantMedium::hit  object.rs:543-575
+            const uint2 fr = sc.frames[f2u(ia.w) >> 4];
+            V3 mo = fo, md = fd;
+            for (uint32_t k = f_nops; k < fr.y; ++k) apply_op_ray(sc.ops[fr.x + k], mo, md, st.rtime);
+            const float4 ba = sc.items[2u * i + 2u], bb = sc.items[2u * i + 3u];
+            float t1, t2;
+            if (prim_hit_t(sc, ba, bb, mo, md, st.rtime, fr.y, kF32Min, kF32Max, t1) &&
+                prim_hit_t(sc, ba, bb, mo, md, st.rtime, fr.y, t1 + 0.0001f, kF32Max, t2)) {
+                t1 = rt_max(t1, kNear);
+                t2 = rt_min(t2, best_t);
+                if (!(t1 >= t2)) {
+                    const float len = length(md);
+                    const float distance_inside = (t2 - t1) * len;
+                    const U4 mw = st.rng.block(st.bounce, PURPOSE_MEDIUM0 + f2u(ia.y), 0u);
+                    const float hit_distance = -(1.f / ia.x) * ln_f32(unit_f32(mw.x));
+                    if (hit_distance < distance_inside) {
+                        best_t = t1 + hit_distance / len;
+                        best = i;
+                    }
+                }
+            }
+            i += 2u;
+        } else if (kind == IT_SET_FRAME) {
+            if (kFrames) {
+                const uint2 fr = sc.frames[f2u(ia.w) >> 4];
+                fo = st.ro;
+                fd = st.rd;
+                for (uint32_t k = 0; k < fr.y; ++k) apply_op_ray(sc.ops[fr.x + k], fo, fd, st.rtime);
+                f_nops = fr.y;
+                inv = mk(1.f / fd.x, 1.f / fd.y, 1.f / fd.z);
+            }
+            i += 1u;
+        } else {
+            break;  // IT_END
+        }
+    }
+    best_t_out = best_t;
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The body of color()'s loop after hit_top (lib.rs:73-98).  Returns true when the path is finished
+// and `result` holds what color() returns; otherwise st carries the scattered ray.
+// ------------------------------------------------------------------------------------------------
+RT_HD bool shade_and_scatter(const Scene& sc, const KParams& P, PathState& st, uint32_t best, float best_t, V3& result) {
+    result = splat(0.f);
+    if (best == kNoHit) {  // lib.rs:100, or the book-1 sky (rtiow_b200.h RTIOW_BG_SKY_GRADIENT)
+        if (P.bg_kind == 1u) {
+            const V3 unit_direction = into_unit(st.rd);
+            const float t = 0.5f * (unit_direction.y + 1.0f);
+            result = st.strength * ((1.0f - t) * mk(P.bg0[0], P.bg0[1], P.bg0[2]) + t * mk(P.bg1[0], P.bg1[1], P.bg1[2]));
+        }
+        return true;
+    }
+    // ---- rebuild the HitRecord of the winning item (object.rs:61-71) --------------------------
+    const float4 ia = sc.items[2u * best], ib = sc.items[2u * best + 1u];
+    const uint32_t kind = f2u(ia.w) & 15u;
+    const uint32_t flags = f2u(ib.w) >> 24;
+    const uint2 fr = sc.frames[f2u(ia.w) >> 4];
+    V3 lo = st.ro, ld = st.rd;
+    for (uint32_t k = 0; k < fr.y; ++k) apply_op_ray(sc.ops[fr.x + k], lo, ld, st.rtime);
+    V3 p, n;
+    if (kind == IT_SPHERE) {
+        if (flags & FL_HAS_OFFSET) lo = lo - mk(ib.x, ib.y, ib.z);
+        p = lo + best_t * ld;  // ray.point_at_parameter(t)  object.rs:100
+        n = p / ia.x;          // object.rs:104
+        if (flags & FL_FLIP) n = -n;
+        if (flags & FL_HAS_OFFSET) p = p + mk(ib.x, ib.y, ib.z);
+    } else if (kind == IT_RECT) {
+        p = lo + best_t * ld;  // object.rs:209
+        const uint32_t axis = (flags >> 2) & 3u;
+        n = mk(axis == 0 ? 1.f : 0.f, axis == 1 ? 1.f : 0.f, axis == 2 ? 1.f : 0.f);
+        if (flags & FL_FLIP) n = -n;
+    } else {                   // medium  object.rs:565-570
+        p = lo + best_t * ld;
+        n = mk(1.f, 0.f, 0.f);
+    }
+    for (uint32_t k = fr.y; k > 0u; --k) apply_op_hit(sc.ops[fr.x + k - 1u], p, n);
+
+    const uint32_t mat_id = f2u(ib.w) & 0x00ffffffu;
+    const float4 m0 = sc.mats[2u * mat_id], m1 = sc.mats[2u * mat_id + 1u];
+    const uint32_t mkind = f2u(m0.x) & 0xffu;
+    const V3 rd = st.rd;
+    bool done = false;
+    if (mkind == MAT_DIFFUSE_LIGHT) {
+        // accum = accum + strength * (brightness * emission(p)); no scatter -> return accum  (lib.rs:76,88-91)
+        result = splat(0.f) + st.strength * (m0.z * material_texture(sc, m0, m1, p));
+        return true;
+    } else if (mkind == MAT_LAMBERTIAN) {      // material.rs:57-65
+        const V3 target = p + n + in_unit_sphere(st.rng, st.bounce);
+        st.rd = target - p;
+        st.ro = p;
+        st.strength = st.strength * material_texture(sc, m0, m1, p);
+    } else if (mkind == MAT_METAL) {           // material.rs:66-81
+        const V3 refl = reflect(into_unit(rd), n);
+        st.rd = refl + m0.z * in_unit_sphere(st.rng, st.bounce);
+        st.ro = p;
+        if (dot(st.rd, n) > 0.f) st.strength = st.strength * mk(m1.x, m1.y, m1.z);
+        else done = true;                      // absorbed: return accum (= 0)
+    } else if (mkind == MAT_DIELECTRIC) {      // material.rs:82-107
+        const float ref_idx = m0.z;
+        V3 outward_normal;
+        float ni_over_nt, cosine;
+        const float ddn = dot(rd, n);
+        if (ddn > 0.f) {
+            outward_normal = -n;
+            ni_over_nt = ref_idx;
+            cosine = ref_idx * ddn / length(rd);
+        } else {
+            outward_normal = n;
+            ni_over_nt = 1.0f / ref_idx;
+            cosine = -ddn / length(rd);
+        }
+        V3 direction;
+        bool refracted = refract(rd, outward_normal, ni_over_nt, direction);
+        if (refracted) {  // the draw happens only when refract() is Some (material.rs:96-97)
+            const U4 w = st.rng.block(st.bounce, PURPOSE_SCATTER, 0u);
+            if (!(unit_f32(w.x) >= schlick(cosine, ref_idx))) refracted = false;
+        }
+        if (!refracted) direction = reflect(rd, n);
+        st.rd = direction;
+        st.ro = p;
+        st.strength = st.strength * splat(1.f);
+    } else {                                   // Isotropic  material.rs:109-116
+        st.rd = in_unit_sphere(st.rng, st.bounce);
+        st.ro = p;
+        st.strength = st.strength * material_texture(sc, m0, m1, p);
+    }
+    if (!done) {
+        if (st.bounce == 50u) done = true;     // lib.rs:93-95 (accum is 0 here)
+        else st.bounce += 1u;
+    }
+    return done;
+}
+
+}  // namespace rtiow

@@ -1,0 +1,192 @@
+// The sm_100a path-tracing megakernel: one launch runs the reference's whole par_cast body
+// (src/lib.rs:363-376) for a block of scanlines and a range of samples:
+//   Camera::get_ray (camera.rs:52-63) -> color (lib.rs:60-101) -> hit_top (lib.rs:33-55) ->
+//   Bvh::hit / Aabb::hit (bvh.rs:85-120, aabb.rs:18-29) -> Object::hit (object.rs) ->
+//   Material::scatter / emitted (material.rs:55-128) -> Texture (texture.rs) -> perlin (perlin.rs)
+// The per-path arithmetic lives in path_logic.cuh; this file is the execution model:
+//  * persistent grid (a multiple of the SM count); each CTA first stages the whole scene blob
+//    into shared memory with TMA bulk copies (cp.async.bulk + mbarrier) when it fits;
+//  * one warp lane = one pixel-sample in flight.  A warp owns a group of 32 neighbouring pixels
+//    and hands their samples to lanes as they fall idle (__ballot_sync + prefix popcount), so
+//    lanes stay busy although path lengths differ wildly; groups come from a global counter;
+//  * the object tree is a stack-less "threaded" stream in the reference's visiting order, so a
+//    lane's traversal state is just a cursor and the nearest hit so far;
+//  * per-sample radiance goes to a staging buffer with one 16-byte store; a second kernel folds
+//    the samples of each pixel left to right exactly like `.sum()` (vec3.rs:195-203).
+#pragma once
+#include "path_logic.cuh"
+
+namespace rtiow {
+
+// ------------------------------------------------------------------------------------------------
+// TMA staging of the scene blob
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void stage_scene_tma(unsigned char* smem_dst, const unsigned char* gsrc, uint32_t bytes,
+                                                uint64_t* mbar) {
+    const uint32_t bar = smem_u32(mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        const uint32_t kChunk = 16384;  // a multiple of 128 B; blob sections are 128 B aligned
+        for (uint32_t off = 0; off < bytes; off += kChunk) {
+            uint32_t n = bytes - off < kChunk ? bytes - off : kChunk;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(smem_dst + off)),
+                         "l"(gsrc + off), "r"(n), "r"(bar)
+                         : "memory");
+        }
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar)
+            : "memory");
+    }
+}
+
+template <bool kSmem, bool kFrames, int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __grid_constant__ KParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+
+    const unsigned char* base;
+    if constexpr (kSmem) {
+        stage_scene_tma(smem_raw, P.blob, P.blob_bytes, &mbar);
+        base = smem_raw;
+    } else {
+        base = P.blob;
+    }
+    const Scene sc = scene_views(base, P);
+
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    // ---- warp-uniform job pool: the samples of one 32-pixel group ----------------------------
+    uint32_t pool_base = 0, pool_valid = 32, pool_next = 0, pool_end = 0;
+    bool exhausted = false;
+
+    // ---- per-lane path state ------------------------------------------------------------------
+    bool active = false;
+    PathState st;
+    st.pix = 0; st.samp = 0; st.bounce = 0;
+    st.ro = splat(0.f); st.rd = splat(0.f); st.strength = splat(1.f);
+    st.rtime = 0.f;
+    st.rng = Rng{P.key0, P.key1, 0u, 0u};
+
+    for (;;) {
+        // ============ 1. hand new pixel-samples to idle lanes (ballot + prefix popcount) ========
+        const bool need = !active;
+        const uint32_t need_mask = __ballot_sync(0xffffffffu, need);
+        bool fresh = false;
+        if (need_mask != 0u && !exhausted) {
+            uint32_t my_rank = __popc(need_mask & lt_mask);
+            uint32_t remaining = __popc(need_mask);
+            for (;;) {
+                const uint32_t avail = pool_end - pool_next;
+                if (need && !fresh && my_rank < avail) {
+                    const uint32_t job = pool_next + my_rank;
+                    st.samp = P.s_begin + job / pool_valid;
+                    st.pix = pool_base + job % pool_valid;
+                    fresh = true;
+                }
+                const uint32_t taken = remaining < avail ? remaining : avail;
+                pool_next += taken;
+                remaining -= taken;
+                my_rank -= taken;  // only meaningful for lanes still waiting
+                if (remaining == 0u) break;
+                uint32_t g = 0;
+                if (lane == 0) g = atomicAdd(P.work_counter, 1u);
+                g = __shfl_sync(0xffffffffu, g, 0);
+                if (g >= P.n_groups) { exhausted = true; break; }
+                pool_base = g * 32u;
+                pool_valid = P.npix - pool_base < 32u ? P.npix - pool_base : 32u;
+                pool_next = 0u;
+                pool_end = pool_valid * P.s_count;
+            }
+        }
+        if (fresh) {
+            generate_camera_ray(P, st);
+            active = true;
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u) break;
+
+        if (active) {
+            // ============ 2. World::hit_top ========================================================
+            float best_t;
+            const uint32_t best = hit_top_stream<kFrames>(sc, st, best_t);
+            // ============ 3. emitted + scatter =====================================================
+            const uint32_t segs = st.bounce + 1u;
+            V3 result;
+            if (shade_and_scatter(sc, P, st, best, best_t, result)) {
+                // one 16-byte store per pixel-sample (st.global.v4.f32)
+                P.staging[static_cast<size_t>(st.samp - P.s_begin) * P.npix + st.pix] =
+                    make_float4(result.x, result.y, result.z, static_cast<float>(segs));
+                active = false;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fold kernel: `(0..ns).map(..).sum()` then `col / ns as f32` (lib.rs:365-374, vec3.rs:195-203).
+// One thread per pixel walks its samples in order; staging is [sample][pixel] so a warp reads
+// 512 contiguous bytes per sample.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fold_kernel(const float4* __restrict__ staging, float4* __restrict__ accum,
+                                                   float* __restrict__ out_rgb, uint32_t npix, uint32_t s_count,
+                                                   int first_pass, int last_pass, float ns_f,
+                                                   unsigned long long* __restrict__ seg_total) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    float segs = 0.f;
+    if (p < npix) {
+        float4 acc = first_pass ? make_float4(0.f, 0.f, 0.f, 0.f) : accum[p];
+        for (uint32_t s = 0; s < s_count; ++s) {
+            const float4 v = __ldcs(staging + static_cast<size_t>(s) * npix + p);
+            acc.x = acc.x + v.x;
+            acc.y = acc.y + v.y;
+            acc.z = acc.z + v.z;
+            segs += v.w;
+        }
+        if (last_pass) {
+            out_rgb[3u * p + 0u] = acc.x / ns_f;
+            out_rgb[3u * p + 1u] = acc.y / ns_f;
+            out_rgb[3u * p + 2u] = acc.z / ns_f;
+        } else {
+            accum[p] = acc;
+        }
+    }
+    // segments are small integers: exact in f32 up to 2^24 per pixel-pass
+    unsigned long long w = static_cast<unsigned long long>(segs);
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if ((threadIdx.x & 31u) == 0u && w) atomicAdd(seg_total, w);
+}
+
+// Per-sample export for parity debugging: staging [s][pix] -> out [pix][ns_total][4]
+__global__ void __launch_bounds__(256) export_samples_kernel(const float4* __restrict__ staging, float4* __restrict__ out,
+                                                             uint32_t npix, uint32_t s_begin, uint32_t s_count,
+                                                             uint32_t ns_total) {
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<size_t>(npix) * s_count) return;
+    const uint32_t s = static_cast<uint32_t>(idx / npix), p = static_cast<uint32_t>(idx % npix);
+    out[static_cast<size_t>(p) * ns_total + s_begin + s] = staging[idx];
+}
+
+// print_ppm's quantiser (lib.rs:344-361): sqrt, then ((255.99 * x) as i32).max(0).min(255)
+__global__ void __launch_bounds__(256) ppm_quantise_kernel(const float* __restrict__ in, unsigned char* __restrict__ out, size_t n) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int v = __float2int_rz(255.99f * sqrtf(in[i]));  // saturating, NaN -> 0, like Rust `as i32`
+    out[i] = static_cast<unsigned char>(min(max(v, 0), 255));
+}
+
+}  // namespace rtiow

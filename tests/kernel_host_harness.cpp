@@ -1,0 +1,65 @@
+// TEST INFRASTRUCTURE — never linked into the shipped libraries.
+//
+// Compiles the megakernel's per-path code (rtiow-rust_b200/csrc/device/path_logic.cuh: camera ray,
+// threaded-stream hit_top, shading) for the HOST and runs it pixel-sample by pixel-sample over a
+// flattened scene descriptor, with the same blob layout the device uses.  Comparing its output
+// with the oracle isolates flattener / stream-logic bugs from CUDA-specific ones, and can be done
+// in the CPU-only container.  The GPU parity tests (-m gpu) check the real kernel.
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../rtiow-rust_b200/csrc/abi/scene_blob.hpp"
+#include "../rtiow-rust_b200/csrc/device/path_logic.cuh"
+
+extern "C" int harness_render(const rtiow_scene_desc_t* desc, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny,
+                              uint32_t ns, uint64_t seed, uint32_t row_begin, uint32_t row_end, float* out_rgb,
+                              float* out_samples) {
+    using namespace rtiow;
+    bool has_frames = false, uses_perlin = false;
+    std::string msg;
+    if (int rc = validate_desc(desc, &has_frames, &uses_perlin, &msg)) return rc;
+    BlobLayout lay{};
+    const std::vector<unsigned char> blob = build_blob(desc, uses_perlin, &lay);
+    KParams P{};
+    P.blob = blob.data();
+    P.blob_bytes = static_cast<uint32_t>(blob.size());
+    P.off_frames = lay.off_frames; P.off_ops = lay.off_ops; P.off_mats = lay.off_mats; P.off_tex = lay.off_tex;
+    P.off_pvecs = lay.off_pvecs; P.off_pperm = lay.off_pperm;
+    std::memcpy(P.cam, cam, sizeof(float) * 21);
+    P.nx = nx; P.ny = ny; P.row_begin = row_begin; P.n_rows = row_end - row_begin;
+    P.s_begin = 0; P.s_count = ns;
+    P.npix = P.n_rows * nx;
+    P.key0 = static_cast<uint32_t>(seed); P.key1 = static_cast<uint32_t>(seed >> 32);
+    P.bg_kind = desc->background_kind;
+    std::memcpy(P.bg0, desc->background_c0, 12);
+    std::memcpy(P.bg1, desc->background_c1, 12);
+    const Scene sc = scene_views(blob.data(), P);
+    for (uint32_t pix = 0; pix < P.npix; ++pix) {
+        float acc[3] = {0.f, 0.f, 0.f};
+        for (uint32_t s = 0; s < ns; ++s) {
+            PathState st;
+            st.pix = pix; st.samp = s;
+            st.rng = Rng{P.key0, P.key1, 0u, 0u};
+            generate_camera_ray(P, st);
+            V3 result;
+            uint32_t segs;
+            for (;;) {
+                float best_t;
+                const uint32_t best = has_frames ? hit_top_stream<true>(sc, st, best_t) : hit_top_stream<false>(sc, st, best_t);
+                segs = st.bounce + 1u;
+                if (shade_and_scatter(sc, P, st, best, best_t, result)) break;
+            }
+            if (out_samples) {
+                float* o = out_samples + (static_cast<size_t>(pix) * ns + s) * 4;
+                o[0] = result.x; o[1] = result.y; o[2] = result.z; o[3] = static_cast<float>(segs);
+            }
+            acc[0] = acc[0] + result.x; acc[1] = acc[1] + result.y; acc[2] = acc[2] + result.z;
+        }
+        if (out_rgb) {
+            const float nsf = static_cast<float>(ns);
+            out_rgb[3 * pix] = acc[0] / nsf; out_rgb[3 * pix + 1] = acc[1] / nsf; out_rgb[3 * pix + 2] = acc[2] / nsf;
+        }
+    }
+    return 0;
+}
