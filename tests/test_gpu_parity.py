@@ -1,0 +1,168 @@
+"""Parity tests proper: the sm_100a megakernel, called through the C ABI, against the CPU oracle
+and the committed golden fixtures.  Bar: BIT-EXACT — every f32 of every pixel (and of every
+per-sample radiance) identical; the kernel is compiled without FMA contraction and follows the
+reference's operation order, so any differing float is a bug.  Run on the B200 box: pytest -m gpu."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import rtiow_rust_b200 as R
+from rtiow_rust_b200 import _native as N
+from rtiow_rust_b200 import api
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from common import bits_equal, golden_cases, n_diff  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+NT = os.cpu_count() or 4
+
+
+def test_extension_is_loaded_and_device_is_b200():
+    import torch
+    assert torch.cuda.is_available()
+    assert torch.cuda.get_device_capability(0)[0] == 10
+    world, cam = R.build_scene("cornell", 16, 16, use_bvh=False)
+    R.par_cast(16, 16, 2, cam, world)
+    st = world.stats()
+    assert st["kernel_launches"] == 2 and st["scene_in_smem"] == 1 and st["samples"] == 16 * 16 * 2
+    loaded = open("/proc/self/maps").read()
+    assert "librtiow_b200.so" in loaded and "librtiow_host.so" in loaded
+
+
+def test_golden_fixtures_bit_exact():
+    for key, name, nx, ny, ns, bvh, want, segs in golden_cases():
+        world, cam = R.build_scene(name, nx, ny, use_bvh=bvh)
+        got = R.par_cast(nx, ny, ns, cam, world).rgb
+        assert n_diff(got, want) == 0, key
+        assert world.stats()["segments"] == segs, key      # same number of hit_top calls as the oracle
+
+
+@pytest.mark.parametrize("name", R.SCENES)
+@pytest.mark.parametrize("bvh", [False, True])
+def test_every_scene_per_sample_bit_exact(oracle, name, bvh):
+    nx, ny, ns = (64, 48, 8) if not (name in ("simple_light", "book1", "book1_head") and not bvh) else (32, 24, 4)
+    world, cam = R.build_scene(name, nx, ny, use_bvh=bvh)
+    smp = api.render_samples(nx, ny, ns, cam, world, seed=2024)
+    img = R.par_cast(nx, ny, ns, cam, world, seed=2024).rgb
+    oimg, osmp, cnt = oracle.Scene(name, nx, ny, top_level_bvh=bvh).render(ns, seed=2024, nthreads=NT, want_samples=True,
+                                                                          want_counters=True)
+    assert n_diff(smp[..., :3], osmp) == 0
+    assert int(smp[..., 3].sum()) == cnt["segments"]
+    assert n_diff(img, oimg) == 0
+
+
+def test_c1_book1_400x200x10_bit_exact(oracle):
+    """BASELINE.json configs[0]: the reference's own CPU-runnable case."""
+    world, cam = R.build_scene("book1", 400, 200)
+    got = R.par_cast(400, 200, 10, cam, world).rgb
+    want, _, cnt = oracle.Scene("book1", 400, 200).render(10, nthreads=NT, want_counters=True)
+    assert n_diff(got, want) == 0
+    assert world.stats()["segments"] == cnt["segments"]
+    q = api.ppm_bytes(got, world)
+    assert np.array_equal(q.astype(np.int32), oracle.ppm_quantise(want))      # the PPM the Rust binary would print
+
+
+@pytest.mark.parametrize("name,bvh", [("cornell", False), ("final", False)])
+def test_reduced_c3_c4_100x100x16_bit_exact(oracle, name, bvh):
+    world, cam = R.build_scene(name, 100, 100, use_bvh=bvh)
+    got = R.par_cast(100, 100, 16, cam, world).rgb
+    want, _, _ = oracle.Scene(name, 100, 100, top_level_bvh=bvh).render(16, nthreads=NT)
+    assert n_diff(got, want) == 0
+
+
+def test_row_blocks_are_bit_identical_to_the_full_image():
+    """Multi-GPU sharding unit: any row range equals the same rows of the whole image."""
+    nx, ny, ns = 96, 70, 6
+    world, cam = R.build_scene("final", nx, ny, use_bvh=False)
+    full = R.par_cast(nx, ny, ns, cam, world).rgb
+    for r0, r1 in ((0, 35), (35, 70), (0, 1), (69, 70), (13, 50)):
+        part = R.par_cast(nx, ny, ns, cam, world, rows=(r0, r1)).rgb
+        assert bits_equal(part, full[r0:r1]), (r0, r1)
+
+
+def test_execution_shape_does_not_change_results():
+    """Sample passes, CTA size, residency (shared vs global memory) and occupancy are scheduling
+    only: the image must not move by one bit."""
+    nx, ny, ns = 80, 60, 40
+    world, cam = R.build_scene("kitchen_sink", nx, ny, use_bvh=True)
+    ref = R.par_cast(nx, ny, ns, cam, world).rgb
+    assert world.stats()["passes"] == 1
+    world.set_tuning(staging_mib=1)                      # 1 MiB staging -> 80*60*16 B per sample -> 13 samples/pass
+    multi = R.par_cast(nx, ny, ns, cam, world).rgb
+    assert world.stats()["passes"] > 1 and bits_equal(multi, ref)
+    world.set_tuning(staging_mib=2048)
+    for threads in (128, 512):
+        world.set_tuning(cta_threads=threads)
+        assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, ref), threads
+    world.set_tuning(cta_threads=256, force_global=True)
+    assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, ref)
+    assert world.stats()["scene_in_smem"] == 0
+    world.set_tuning(ctas_per_sm=1)
+    assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, ref)
+
+
+def test_determinism_and_seed():
+    world, cam = R.build_scene("book1", 64, 32)
+    a = R.par_cast(64, 32, 8, cam, world, seed=7).rgb
+    assert bits_equal(a, R.par_cast(64, 32, 8, cam, world, seed=7).rgb)
+    assert not bits_equal(a, R.par_cast(64, 32, 8, cam, world, seed=8).rgb)
+    assert bits_equal(a, R.cast(64, 32, 8, cam, world, seed=7).rgb)          # cast == par_cast
+
+
+def test_ragged_and_tiny_images(oracle):
+    """Pixel counts that are not multiples of the 32-pixel warp group, single pixels, single samples."""
+    for nx, ny, ns in ((1, 1, 1), (1, 1, 33), (33, 1, 3), (5, 7, 2), (31, 3, 1)):
+        world, cam = R.build_scene("cornell", nx, ny, use_bvh=False)
+        got = R.par_cast(nx, ny, ns, cam, world).rgb
+        want, _, _ = oracle.Scene("cornell", nx, ny, top_level_bvh=False).render(ns)
+        assert n_diff(got, want) == 0, (nx, ny, ns)
+
+
+def test_device_resident_output_path():
+    import torch
+    nx, ny, ns = 64, 40, 4
+    world, cam = R.build_scene("book1", nx, ny)
+    host = R.par_cast(nx, ny, ns, cam, world).rgb
+    out = torch.empty((ny, nx, 3), dtype=torch.float32, device="cuda:0")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        api.render_rows_device(nx, ny, ns, cam, world, out, (0, ny))
+    s.synchronize()
+    assert bits_equal(out.cpu().numpy(), host)
+
+
+def test_error_behaviour():
+    world, cam = R.build_scene("cornell", 8, 8, use_bvh=False)
+    with pytest.raises(R.RtiowError) as e:
+        R.par_cast(8, 8, 0, cam, world)
+    assert e.value.code == N.ERR_INVALID_ARG
+    with pytest.raises(R.RtiowError):
+        R.par_cast(8, 8, 1, cam, world, rows=(4, 4))
+    with pytest.raises(R.RtiowError):
+        R.par_cast(8, 8, 1, cam, world, rows=(0, 9))
+    bad = R.Camera.look((0, 0, 1), (0, 0, 0), (0, 1, 0), 40.0, 1.0, 0.0, 1.0, (1.0, 1.0))
+    with pytest.raises(R.RtiowError) as e:      # rand's gen_range panics on an empty range (camera.rs:55)
+        R.par_cast(8, 8, 1, bad, world)
+    assert "low >= high" in str(e.value)
+    with pytest.raises(R.RtiowError):
+        world.set_tuning(cta_threads=96)
+
+
+def test_c2_full_size_properties(oracle):
+    """BASELINE.json configs[1] at full size (1200x800x50 = 48 M samples): scanline bands against the
+    oracle float-for-float, plus size-independent properties of the whole frame."""
+    nx, ny, ns = 1200, 800, 50
+    world, cam = R.build_scene("book1", nx, ny)
+    full = R.par_cast(nx, ny, ns, cam, world).rgb
+    st = world.stats()
+    assert st["samples"] == nx * ny * ns
+    sc = oracle.Scene("book1", nx, ny)
+    for r0 in (0, 397, 640, 796):                     # sky, horizon, spheres, bottom edge
+        want, _, _ = sc.render(ns, rows=(r0, r0 + 4), nthreads=NT)
+        assert n_diff(full[r0:r0 + 4], want) == 0, r0
+    assert np.isfinite(full).all() and full.min() >= 0.0
+    halves = [R.par_cast(nx, ny, ns, cam, world, rows=(0, 400)).rgb, R.par_cast(nx, ny, ns, cam, world, rows=(400, 800)).rgb]
+    assert bits_equal(np.concatenate(halves), full)   # sharding is exact
+    assert 2.0 < st["segments"] / st["samples"] < 3.2

@@ -1,0 +1,194 @@
+"""CPU-side tests of the product's host layer (no GPU): the C ABI library loads and exports every
+declared symbol, scene validation, the C++ host mirror's flattener, and — through the host-compiled
+copy of the kernel's per-path code (tests/kernel_host_harness.cpp) — that flattened scenes traverse
+and shade exactly like the oracle's object tree."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import rtiow_rust_b200 as R
+from rtiow_rust_b200 import _native as N
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import harness_lib as H  # noqa: E402
+from common import bits_equal, golden_cases, n_diff  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "rtiow_b200.h")).read()
+    declared = set(re.findall(r"\b(rtiow_b200_\w+)\s*\(", header))
+    assert declared == set(N.ABI_SYMBOLS)
+    lib = N.abi()
+    for sym in declared:
+        assert getattr(lib, sym) is not None
+    assert lib.rtiow_b200_abi_version() == 1
+    nm = subprocess.run(["nm", "-D", "--defined-only", N.ABI_LIB], capture_output=True, text=True).stdout
+    for sym in declared:
+        assert re.search(rf"\bT {sym}\b", nm), sym
+
+
+def test_abi_struct_sizes_match_header():
+    assert C.sizeof(N.Item) == 32 and C.sizeof(N.XformOp) == 16 and C.sizeof(N.Frame) == 8
+    assert C.sizeof(N.MaterialRec) == 32 and C.sizeof(N.TextureRec) == 32 and C.sizeof(N.CameraRec) == 84
+
+
+def test_kernels_are_compiled_for_sm_100a_with_tma():
+    log = open(os.path.join(N.BUILD_DIR, "ptxas.log")).read()
+    assert "for 'sm_100a'" in log and "render_kernel" in log
+    assert "bytes spill stores" in log and re.search(r"[1-9]\d* bytes spill stores", log) is None
+    sass = subprocess.run(["cuobjdump", "-sass", N.ABI_LIB], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass          # cp.async.bulk (TMA bulk copy) staging of the scene blob
+    assert "SYNCS" in sass           # mbarrier expect_tx / try_wait
+    assert "STG.E.128" in sass       # 16-byte staging store per pixel-sample
+    assert "VOTE" in sass            # __ballot_sync job hand-out
+
+
+def test_no_gpu_means_error_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    world, cam = R.build_scene("cornell", 8, 8, use_bvh=False)
+    with pytest.raises(R.RtiowError) as e:
+        R.par_cast(8, 8, 1, cam, world)
+    assert e.value.code == N.ERR_NO_DEVICE and "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_touch_the_oracle():
+    pkg = os.path.join(ROOT, "rtiow-rust_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "_build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cpp", ".hpp", ".cu", ".cuh", ".h")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"^\s*(#include|import|from)\b.*oracle", text, re.M), os.path.join(dirpath, f)
+                assert "liboracle" not in text
+
+
+@pytest.mark.parametrize("name", R.SCENES)
+def test_every_scene_flattens_and_validates(name):
+    for bvh in (False, True):
+        world, cam = R.build_scene(name, 32, 32, use_bvh=bvh)
+        world.validate()
+        c = world.counts()
+        items = world.items()
+        assert (items[-1, 3] & 15) == 0                       # END
+        kinds = items[:, 3] & 15
+        skips = items[kinds == 1, 3] >> 4
+        assert (skips > np.nonzero(kinds == 1)[0]).all()      # skip links only point forward
+        if bvh:
+            assert c["bbox"] >= 2 * len(world) - 1
+
+
+def test_book1_stream_shape():
+    world, _ = R.build_scene("book1", 400, 200)
+    c = world.counts()
+    n = len(world)
+    assert c["spheres"] == n and c["bbox"] == 2 * n - 1 and c["items"] == 3 * n      # + END - 1
+    assert c["frames"] == 1 and c["ops"] == 0      # every Translate{Sphere} is folded into its item
+    assert c["background"] == 1
+
+
+def test_final_scene_stream_shape():
+    world, _ = R.build_scene("final", 64, 64, use_bvh=False)
+    c = world.counts()
+    assert c["rects"] == 2401 and c["spheres"] == 1007 and c["media"] == 2 and c["set_frames"] == 2
+    assert c["bbox"] == 799 + 1999
+
+
+def _desc_copy(world):
+    d = N.SceneDesc()
+    C.memmove(C.byref(d), world.desc, C.sizeof(d))
+    return d
+
+
+def test_validation_rejects_malformed_scenes():
+    world, _ = R.build_scene("cornell", 16, 16, use_bvh=True)
+    lib = N.abi()
+
+    def expect(desc, code, fragment):
+        assert lib.rtiow_b200_scene_validate(C.byref(desc)) == code
+        assert fragment in lib.rtiow_b200_last_error().decode()
+
+    d = _desc_copy(world)
+    assert lib.rtiow_b200_scene_validate(C.byref(d)) == 0
+    d.abi_version = 99
+    expect(d, N.ERR_INVALID_ARG, "abi_version")
+    d = _desc_copy(world)
+    d.n_items -= 1                                      # drops END
+    expect(d, N.ERR_INVALID_SCENE, "END")
+    d = _desc_copy(world)
+    d.n_items = 0
+    expect(d, N.ERR_INVALID_SCENE, "zero items")        # cf. "Can't create a BVH from zero objects." (bvh.rs:60)
+    # a backward skip link would let traversal loop forever on the device
+    items = (N.Item * world.desc.contents.n_items)()
+    C.memmove(items, world.desc.contents.items, C.sizeof(items))
+    d = _desc_copy(world)
+    d.items = items
+    assert (items[0].a_w & 15) == 1
+    items[0].a_w = 1 | (0 << 4)
+    expect(d, N.ERR_INVALID_SCENE, "forward")
+    C.memmove(items, world.desc.contents.items, C.sizeof(items))
+    rect = next(i for i in range(len(items)) if (items[i].a_w & 15) == 3)
+    items[rect].b_w = (items[rect].b_w & 0xFF000000) | 0x00FFFFFF
+    expect(d, N.ERR_INVALID_SCENE, "material")
+    assert lib.rtiow_b200_scene_validate(None) == N.ERR_INVALID_ARG
+
+
+def test_unknown_scene_and_camera_look():
+    with pytest.raises(RuntimeError):
+        R.build_scene("nope", 8, 8)
+    cam = R.Camera.look((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 2.0, 0.1, 10.0).as_array()
+    assert list(cam[0:3]) == [13, 2, 3] and cam[18] == np.float32(0.05)
+
+
+def test_camera_matches_oracle(oracle):
+    for name in ("book1", "cornell", "final", "kitchen_sink"):
+        _, cam = R.build_scene(name, 120, 80)
+        assert np.array_equal(cam.as_array(), oracle.Scene(name, 120, 80).camera()), name
+    a = R.Camera.look((1, 2, 3), (4, -5, 6), (0, 1, 0), 33.0, 1.5, 0.3, 7.0, (0.25, 0.75)).as_array()
+    b = oracle.camera_look((1, 2, 3), (4, -5, 6), (0, 1, 0), 33.0, 1.5, 0.3, 7.0, 0.25, 0.75)
+    assert np.array_equal(a, b)
+
+
+def test_oracle_still_matches_golden(oracle):
+    for key, name, nx, ny, ns, bvh, want, segs in golden_cases():
+        got, _, cnt = oracle.Scene(name, nx, ny, top_level_bvh=bvh).render(ns, nthreads=4, want_counters=True)
+        assert bits_equal(got, want), key
+        assert cnt["segments"] == segs
+
+
+def test_flattened_stream_logic_matches_golden():
+    """The kernel's per-path code, compiled for the host, over the product's flattened scenes."""
+    for key, name, nx, ny, ns, bvh, want, segs in golden_cases():
+        world, cam = R.build_scene(name, nx, ny, use_bvh=bvh)
+        got, smp = H.render(world, cam, nx, ny, ns, want_samples=True)
+        assert n_diff(got, want) == 0, key
+        assert int(smp[..., 3].sum()) == segs, key
+
+
+@pytest.mark.parametrize("name,bvh", [("book1", True), ("cornell", False), ("final", False), ("final", True),
+                                      ("kitchen_sink", True), ("kitchen_sink", False), ("volume_test", False)])
+def test_flattened_stream_logic_matches_oracle_per_sample(oracle, name, bvh):
+    nx, ny, ns = 40, 30, 5
+    world, cam = R.build_scene(name, nx, ny, use_bvh=bvh)
+    _, smp = H.render(world, cam, nx, ny, ns, seed=12345, want_samples=True)
+    _, osmp, cnt = oracle.Scene(name, nx, ny, top_level_bvh=bvh).render(ns, seed=12345, nthreads=4, want_samples=True,
+                                                                       want_counters=True)
+    assert n_diff(smp[..., :3], osmp) == 0
+    assert int(smp[..., 3].sum()) == cnt["segments"]
+
+
+def test_print_ppm_formatting(tmp_path, oracle):
+    rgb = np.array([[[0.25, 1.0, 0.0], [4.0, -1.0, np.nan]]], np.float32)
+    path = tmp_path / "a.ppm"
+    R.print_ppm(R.Image(rgb), path)
+    assert path.read_text() == "P3\n2 1\n255\n127 255 0\n255 0 0\n"      # lib.rs:345,358: one pixel per line
+    assert oracle.ppm_quantise(rgb).reshape(-1).tolist() == [127, 255, 0, 255, 0, 0]
