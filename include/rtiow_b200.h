@@ -169,6 +169,8 @@ typedef struct rtiow_stats_t {
     uint32_t scene_in_smem; /* 1 if the scene blob was staged into shared memory                          */
     uint32_t scene_bytes;
     uint32_t grid, block, dyn_smem_bytes, regs_per_thread;
+    uint32_t accel_nodes;    /* nodes of the library's own index over the scene's Bvh subtrees (0 = none) */
+    uint32_t accel_subtrees; /* how many Bvh subtrees were re-indexed                                      */
 } rtiow_stats_t;
 
 typedef struct rtiow_scene rtiow_scene_t;
@@ -216,6 +218,13 @@ int rtiow_b200_get_stats(rtiow_scene_t* scene, rtiow_stats_t* out);
  * force_global != 0 keeps the scene in global memory even if it fits shared memory. */
 int rtiow_b200_set_tuning(rtiow_scene_t* scene, uint32_t cta_threads, uint32_t ctas_per_sm, uint32_t staging_mib,
                           int force_global);
+
+/* How `Bvh` subtrees (src/bvh.rs) are walked.  Both give the same image bit for bit; the choice is
+ * speed only.  REINDEXED (default): the library indexes the subtree's leaves with its own tree and
+ * visits the nearer child first.  REFERENCE_ORDER: the boxes exactly as flattened, left first, like
+ * Bvh::hit (src/bvh.rs:85-120). */
+enum { RTIOW_TRAVERSAL_REINDEXED = 0, RTIOW_TRAVERSAL_REFERENCE_ORDER = 1 };
+int rtiow_b200_set_traversal(rtiow_scene_t* scene, int mode);
 
 #ifdef __cplusplus
 }

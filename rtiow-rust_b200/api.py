@@ -137,6 +137,10 @@ class World:
     def set_tuning(self, device=0, cta_threads=0, ctas_per_sm=0, staging_mib=0, force_global=False):
         _check(N.abi().rtiow_b200_set_tuning(self.gpu(device), cta_threads, ctas_per_sm, staging_mib, int(force_global)))
 
+    def set_traversal(self, mode, device=0):
+        """0 = re-indexed Bvh subtrees (default), 1 = the reference's own visiting order.  Same image either way."""
+        _check(N.abi().rtiow_b200_set_traversal(self.gpu(device), int(mode)))
+
     def stats(self, device=0):
         st = N.Stats()
         _check(N.abi().rtiow_b200_get_stats(self.gpu(device), C.byref(st)))

@@ -54,9 +54,13 @@ struct rtiow_scene {
     int device = 0;
     int sm_count = 0;
     int max_smem_optin = 0;
-    unsigned char* d_blob = nullptr;
-    uint32_t blob_bytes = 0;
-    uint32_t off_frames = 0, off_ops = 0, off_mats = 0, off_tex = 0, off_pvecs = 0, off_pperm = 0;
+    // [0] = re-indexed Bvh subtrees (default), [1] = the plain reference-order stream
+    struct Blob {
+        unsigned char* d = nullptr;
+        uint32_t bytes = 0;
+        rtiow::BlobLayout lay{};
+    } blobs[2];
+    int traversal = 0;
     bool has_frames = false;
     uint32_t bg_kind = 0;
     float bg0[3] = {0, 0, 0}, bg1[3] = {0, 0, 0};
@@ -134,10 +138,11 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     CK(s->staging.reserve(npix64 * s_pass * 16));
     CK(s->accum.reserve(npix64 * 16));
 
-    const bool fits = s->blob_bytes + 1024u <= static_cast<uint32_t>(s->max_smem_optin);
+    const rtiow_scene::Blob& B = s->blobs[s->traversal];
+    const bool fits = B.bytes + 1024u <= static_cast<uint32_t>(s->max_smem_optin);
     const bool smem = fits && !s->force_global;
     const Variant var = pick_variant(smem, s->has_frames, s->cta_threads);
-    const size_t dyn_smem = smem ? s->blob_bytes : 0;
+    const size_t dyn_smem = smem ? B.bytes : 0;
     CK(cudaFuncSetAttribute(var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem)));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var.fn, var.threads, dyn_smem));
@@ -151,10 +156,10 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     CK(cudaFuncGetAttributes(&fa, var.fn));
 
     KParams P{};
-    P.blob = s->d_blob;
-    P.blob_bytes = s->blob_bytes;
-    P.off_frames = s->off_frames; P.off_ops = s->off_ops; P.off_mats = s->off_mats; P.off_tex = s->off_tex;
-    P.off_pvecs = s->off_pvecs; P.off_pperm = s->off_pperm;
+    P.blob = B.d;
+    P.blob_bytes = B.bytes;
+    P.off_nodes = B.lay.off_nodes; P.off_frames = B.lay.off_frames; P.off_ops = B.lay.off_ops; P.off_mats = B.lay.off_mats;
+    P.off_tex = B.lay.off_tex; P.off_pvecs = B.lay.off_pvecs; P.off_pperm = B.lay.off_pperm;
     std::memcpy(P.cam, cam, sizeof(float) * 21);
     P.nx = nx; P.ny = ny; P.row_begin = r0; P.n_rows = n_rows;
     P.npix = npix; P.n_groups = n_groups;
@@ -198,7 +203,9 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     s->stats.kernel_launches = launches;
     s->stats.passes = n_pass;
     s->stats.scene_in_smem = smem ? 1u : 0u;
-    s->stats.scene_bytes = s->blob_bytes;
+    s->stats.scene_bytes = B.bytes;
+    s->stats.accel_nodes = B.lay.n_nodes;
+    s->stats.accel_subtrees = B.lay.n_accel;
     s->stats.grid = grid;
     s->stats.block = static_cast<uint32_t>(var.threads);
     s->stats.dyn_smem_bytes = static_cast<uint32_t>(dyn_smem);
@@ -243,16 +250,10 @@ int rtiow_b200_scene_create(const rtiow_scene_desc_t* d, int device, rtiow_scene
         return set_err(RTIOW_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
                                                 "; this library carries sm_100a code only");
 
-    // ---- build the device blob: items | frames | ops | materials | textures | perlin vecs | perlin perms
-    rtiow::BlobLayout lay{};
-    const std::vector<unsigned char> blob = rtiow::build_blob(d, uses_perlin, &lay);
     auto s = new rtiow_scene();
     s->device = device;
     s->sm_count = prop.multiProcessorCount;
     s->max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
-    s->off_frames = lay.off_frames; s->off_ops = lay.off_ops; s->off_mats = lay.off_mats; s->off_tex = lay.off_tex;
-    s->off_pvecs = lay.off_pvecs; s->off_pperm = lay.off_pperm;
-    s->blob_bytes = static_cast<uint32_t>(blob.size());
     s->has_frames = has_frames;
     s->bg_kind = d->background_kind;
     std::memcpy(s->bg0, d->background_c0, 12);
@@ -262,8 +263,14 @@ int rtiow_b200_scene_create(const rtiow_scene_desc_t* d, int device, rtiow_scene
         rtiow_b200_scene_destroy(s);
         return set_err(RTIOW_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(ce));
     };
-    if ((e = cudaMalloc(reinterpret_cast<void**>(&s->d_blob), s->blob_bytes)) != cudaSuccess) return fail(e, "cudaMalloc(blob)");
-    if ((e = cudaMemcpy(s->d_blob, blob.data(), s->blob_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e, "cudaMemcpy(blob)");
+    // ---- build the device blobs: items | accel nodes | frames | ops | materials | textures | perlin
+    for (int v = 0; v < 2; ++v) {
+        rtiow_scene::Blob& B = s->blobs[v];
+        const std::vector<unsigned char> blob = rtiow::build_blob(d, uses_perlin, &B.lay, v == 0);
+        B.bytes = static_cast<uint32_t>(blob.size());
+        if ((e = cudaMalloc(reinterpret_cast<void**>(&B.d), B.bytes)) != cudaSuccess) return fail(e, "cudaMalloc(blob)");
+        if ((e = cudaMemcpy(B.d, blob.data(), B.bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e, "cudaMemcpy(blob)");
+    }
     if ((e = cudaMalloc(reinterpret_cast<void**>(&s->d_counter), sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMalloc");
     if ((e = cudaMalloc(reinterpret_cast<void**>(&s->d_segs), sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc");
     if ((e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
@@ -272,6 +279,7 @@ int rtiow_b200_scene_create(const rtiow_scene_desc_t* d, int device, rtiow_scene
     if (const char* env = std::getenv("RTIOW_B200_CTAS_PER_SM")) s->ctas_per_sm = static_cast<uint32_t>(std::atoi(env));
     if (const char* env = std::getenv("RTIOW_B200_STAGING_MIB")) s->staging_mib = static_cast<uint32_t>(std::atoi(env));
     if (const char* env = std::getenv("RTIOW_B200_FORCE_GLOBAL")) s->force_global = std::atoi(env) != 0;
+    if (const char* env = std::getenv("RTIOW_B200_TRAVERSAL")) s->traversal = std::atoi(env) != 0 ? 1 : 0;
     *out = s;
     return RTIOW_OK;
 }
@@ -280,7 +288,8 @@ void rtiow_b200_scene_destroy(rtiow_scene_t* s) {
     if (!s) return;
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();
-    if (s->d_blob) cudaFree(s->d_blob);
+    for (auto& B : s->blobs)
+        if (B.d) cudaFree(B.d);
     if (s->d_counter) cudaFree(s->d_counter);
     if (s->d_segs) cudaFree(s->d_segs);
     s->staging.release(); s->accum.release(); s->out.release(); s->samples.release();
@@ -299,6 +308,14 @@ int rtiow_b200_set_tuning(rtiow_scene_t* s, uint32_t cta_threads, uint32_t ctas_
     s->ctas_per_sm = ctas_per_sm;
     if (staging_mib) s->staging_mib = staging_mib;
     s->force_global = force_global != 0;
+    return RTIOW_OK;
+}
+
+int rtiow_b200_set_traversal(rtiow_scene_t* s, int mode) {
+    if (!s) return set_err(RTIOW_ERR_INVALID_ARG, "null scene");
+    if (mode != RTIOW_TRAVERSAL_REINDEXED && mode != RTIOW_TRAVERSAL_REFERENCE_ORDER)
+        return set_err(RTIOW_ERR_INVALID_ARG, "unknown traversal mode");
+    s->traversal = mode;
     return RTIOW_OK;
 }
 

@@ -7,8 +7,14 @@
 #include <vector>
 
 #include "../../../include/rtiow_b200.h"
+#include "accel_build.hpp"
 
 namespace rtiow {
+
+// Internal item kind (never part of the ABI): a re-indexed Bvh subtree (accel_build.hpp).
+//   a_w = 6 | (skip << 4)   skip = index of the item after the subtree's primitives
+//   a[0] = bits(root node index);  the subtree's primitive items follow, in stream order.
+constexpr uint32_t kItemAccel = 6u;
 
 inline bool ops_prefix(const rtiow_scene_desc_t* d, uint32_t outer, uint32_t inner) {
     // true if frame `outer`'s op list is a prefix of frame `inner`'s
@@ -117,12 +123,109 @@ inline int validate_desc(const rtiow_scene_desc_t* d, bool* has_frames, bool* us
 
 
 struct BlobLayout {
-    uint32_t off_frames, off_ops, off_mats, off_tex, off_pvecs, off_pperm;
+    uint32_t off_nodes, off_frames, off_ops, off_mats, off_tex, off_pvecs, off_pperm;
+    uint32_t n_items, n_nodes, n_accel, accel_depth;
 };
 
-// items | frames | ops | materials | textures | perlin vecs (float4) | perlin perms; every section
-// starts on a 128-byte boundary so the whole blob can be moved with 128 B-granular TMA bulk copies.
-inline std::vector<unsigned char> build_blob(const rtiow_scene_desc_t* d, bool uses_perlin, BlobLayout* lay) {
+// ---------------------------------------------------------------------------------------------
+// Stream compaction + re-indexing.  Every BBOX subtree that consists of boxes and primitives only
+// (no medium, no frame switch) becomes ONE kItemAccel item followed by the subtree's primitive
+// items in their original relative order (so "earlier in the stream" still means "earlier in the
+// reference's visiting order" for tie-breaking), plus a tree of AccelNodes over the reference's
+// own leaf boxes.  Everything else is copied, with skip links remapped.
+// ---------------------------------------------------------------------------------------------
+namespace blob_detail {
+
+struct Compactor {
+    const rtiow_scene_desc_t* d;
+    bool enable_accel;
+    std::vector<rtiow_item_t> out;
+    std::vector<AccelNode> nodes;
+    uint32_t n_accel = 0;
+    int max_depth = 0;
+
+    uint32_t kind(uint32_t i) const { return d->items[i].a_w & 15u; }
+    uint32_t payload(uint32_t i) const { return d->items[i].a_w >> 4; }
+
+    // Is the subtree of BBOX item i "simple"?  Collects its leaves (box item index, prim range).
+    struct RawLeaf { uint32_t box, first, end; };
+    bool classify(uint32_t i, std::vector<RawLeaf>* leaves) const {
+        const uint32_t s = payload(i);
+        if (i + 1 >= s) return false;
+        if (kind(i + 1) == RTIOW_ITEM_BBOX) {  // inner node: children tile (i, s)
+            uint32_t j = i + 1;
+            while (j < s) {
+                if (kind(j) != RTIOW_ITEM_BBOX || payload(j) > s) return false;
+                if (!classify(j, leaves)) return false;
+                j = payload(j);
+            }
+            return j == s;
+        }
+        for (uint32_t j = i + 1; j < s; ++j)
+            if (kind(j) != RTIOW_ITEM_SPHERE && kind(j) != RTIOW_ITEM_RECT) return false;
+        if (s - (i + 1) > kMaxLeafItems) return false;
+        leaves->push_back(RawLeaf{i, i + 1, s});
+        return true;
+    }
+
+    void run(uint32_t begin, uint32_t end) {
+        uint32_t i = begin;
+        while (i < end) {
+            const uint32_t k = kind(i);
+            if (k == RTIOW_ITEM_BBOX) {
+                const uint32_t s = payload(i);
+                std::vector<RawLeaf> raw;
+                if (enable_accel && s <= end && d->n_items < (1u << 24) && classify(i, &raw)) {
+                    const size_t at = out.size();
+                    out.push_back(rtiow_item_t{});
+                    std::vector<AccelLeaf> leaves;
+                    leaves.reserve(raw.size());
+                    for (const RawLeaf& rl : raw) {  // stream order
+                        AccelLeaf l{};
+                        std::memcpy(l.mn, d->items[rl.box].a, 12);
+                        std::memcpy(l.mx, d->items[rl.box].b, 12);
+                        l.first = static_cast<uint32_t>(out.size());
+                        l.count = rl.end - rl.first;
+                        for (uint32_t j = rl.first; j < rl.end; ++j) out.push_back(d->items[j]);
+                        leaves.push_back(l);
+                    }
+                    int depth = 0;
+                    const uint32_t root = accel_build(leaves, &nodes, &depth);
+                    max_depth = depth > max_depth ? depth : max_depth;
+                    rtiow_item_t& acc = out[at];
+                    acc.a_w = kItemAccel | (static_cast<uint32_t>(out.size()) << 4);
+                    std::memcpy(&acc.a[0], &root, 4);
+                    ++n_accel;
+                    i = s;
+                } else if (s <= end) {  // keep the box on the reference-order stream, recurse inside
+                    const size_t at = out.size();
+                    out.push_back(d->items[i]);
+                    run(i + 1, s);
+                    out[at].a_w = RTIOW_ITEM_BBOX | (static_cast<uint32_t>(out.size()) << 4);
+                    i = s;
+                } else {  // improperly nested skip link (validated to be forward): copy verbatim region
+                    // cannot happen for streams produced by the flatteners; keep semantics by disabling compaction
+                    throw 0;
+                }
+            } else if (k == RTIOW_ITEM_MEDIUM) {
+                out.push_back(d->items[i]);
+                out.push_back(d->items[i + 1]);
+                i += 2;
+            } else {
+                out.push_back(d->items[i]);
+                i += 1;
+            }
+        }
+    }
+};
+
+}  // namespace blob_detail
+
+// items | accel nodes | frames | ops | materials | textures | perlin vecs (float4) | perlin perms;
+// every section starts on a 128-byte boundary so the whole blob can be moved with 128 B-granular
+// TMA bulk copies.
+inline std::vector<unsigned char> build_blob(const rtiow_scene_desc_t* d, bool uses_perlin, BlobLayout* lay,
+                                             bool enable_accel = true) {
     std::vector<unsigned char> blob;
     auto align_up = [](size_t v) { return (v + 127u) / 128u * 128u; };
     auto append = [&](const void* src, size_t bytes) -> uint32_t {
@@ -131,7 +234,19 @@ inline std::vector<unsigned char> build_blob(const rtiow_scene_desc_t* d, bool u
         if (bytes) std::memcpy(blob.data() + off, src, bytes);
         return static_cast<uint32_t>(off);
     };
-    append(d->items, sizeof(rtiow_item_t) * d->n_items);
+    blob_detail::Compactor cp{d, enable_accel, {}, {}};
+    try {
+        cp.run(0, d->n_items);
+    } catch (int) {  // odd nesting: ship the stream as it is
+        cp = blob_detail::Compactor{d, false, {}, {}};
+        cp.out.assign(d->items, d->items + d->n_items);
+    }
+    append(cp.out.data(), sizeof(rtiow_item_t) * cp.out.size());
+    lay->n_items = static_cast<uint32_t>(cp.out.size());
+    lay->off_nodes = append(cp.nodes.data(), sizeof(AccelNode) * cp.nodes.size());
+    lay->n_nodes = static_cast<uint32_t>(cp.nodes.size());
+    lay->n_accel = cp.n_accel;
+    lay->accel_depth = static_cast<uint32_t>(cp.max_depth);
     lay->off_frames = append(d->frames, sizeof(rtiow_frame_t) * d->n_frames);
     lay->off_ops = append(d->ops, sizeof(rtiow_xform_op_t) * d->n_ops);
     {   // materials, with constant textures baked in: {kind | texkind<<8, tex, param, 0} {color/albedo, 0}

@@ -17,7 +17,9 @@ constexpr float kF32Min = -3.402823466e+38f;  // std::f32::MIN
 constexpr uint32_t kNoHit = 0xffffffffu;
 
 // item kinds / flags mirror include/rtiow_b200.h
-enum : uint32_t { IT_END = 0, IT_BBOX = 1, IT_SPHERE = 2, IT_RECT = 3, IT_MEDIUM = 4, IT_SET_FRAME = 5 };
+enum : uint32_t { IT_END = 0, IT_BBOX = 1, IT_SPHERE = 2, IT_RECT = 3, IT_MEDIUM = 4, IT_SET_FRAME = 5, IT_ACCEL = 6 };
+constexpr uint32_t kLinkLeafBit = 0x80000000u, kLinkNone = 0x7fffffffu;  // accel_build.hpp
+constexpr int kStackDepth = 32;
 enum : uint32_t { FL_HAS_OFFSET = 1u, FL_FLIP = 2u };
 enum : uint32_t { OP_TRANSLATE = 0, OP_SCALE = 1, OP_ROTATE_Y = 2, OP_LINEAR_MOVE = 3, OP_FLIP = 4 };
 enum : uint32_t { MAT_LAMBERTIAN = 0, MAT_METAL = 1, MAT_DIELECTRIC = 2, MAT_DIFFUSE_LIGHT = 3, MAT_ISOTROPIC = 4 };
@@ -26,7 +28,7 @@ enum : uint32_t { TEX_CONSTANT = 0, TEX_CHECKER = 1, TEX_PERLIN = 2 };
 struct KParams {
     const unsigned char* blob;  // device scene blob; items start at offset 0
     uint32_t blob_bytes;
-    uint32_t off_frames, off_ops, off_mats, off_tex, off_pvecs, off_pperm;
+    uint32_t off_nodes, off_frames, off_ops, off_mats, off_tex, off_pvecs, off_pperm;
     float cam[21];              // rtiow_camera_t
     uint32_t nx, ny, row_begin, n_rows;
     uint32_t s_begin, s_count;  // samples [s_begin, s_begin + s_count) of every pixel in this pass
@@ -38,26 +40,67 @@ struct KParams {
     unsigned int* work_counter;
 };
 
-// Views into the scene blob (shared or global memory on the device).
-struct Scene {
-    const float4* items;
-    const uint2* frames;
-    const float4* ops;
-    const float4* mats;
-    const float4* tex;
-    const float4* pvecs;
-    const unsigned char* pperm;
+// ------------------------------------------------------------------------------------------------
+// Where the scene blob lives.  The per-path code reads it through one of these accessors (byte
+// offsets into the blob), so the same source runs against shared memory (ld.shared with a 32-bit
+// address: no generic-address arithmetic in the traversal loop), global memory (ld.global.nc, for
+// scenes that do not fit in shared memory) and host memory (tests/kernel_host_harness.cpp).
+// ------------------------------------------------------------------------------------------------
+struct MemPtr {  // generic pointer: host harness
+    const unsigned char* base;
+    RT_HD float4 ld4(uint32_t off) const { return *reinterpret_cast<const float4*>(base + off); }
+    RT_HD uint2 ld2(uint32_t off) const { return *reinterpret_cast<const uint2*>(base + off); }
+    RT_HD uint32_t ld1b(uint32_t off) const { return base[off]; }
+};
+#ifdef __CUDACC__
+struct MemShared {
+    uint32_t base;  // shared-window address of the staged blob
+    __device__ __forceinline__ float4 ld4(uint32_t off) const {
+        float4 v;
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(base + off));
+        return v;
+    }
+    __device__ __forceinline__ uint2 ld2(uint32_t off) const {
+        uint2 v;
+        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(base + off));
+        return v;
+    }
+    __device__ __forceinline__ uint32_t ld1b(uint32_t off) const {
+        uint32_t v;
+        asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + off));
+        return v;
+    }
+};
+struct MemGlobal {
+    const unsigned char* base;
+    __device__ __forceinline__ float4 ld4(uint32_t off) const { return __ldg(reinterpret_cast<const float4*>(base + off)); }
+    __device__ __forceinline__ uint2 ld2(uint32_t off) const { return __ldg(reinterpret_cast<const uint2*>(base + off)); }
+    __device__ __forceinline__ uint32_t ld1b(uint32_t off) const { return __ldg(base + off); }
+};
+#endif
+
+// Views into the scene blob.
+template <class Mem>
+struct SceneT {
+    Mem m;
+    uint32_t off_nodes, off_frames, off_ops, off_mats, off_tex, off_pvecs, off_pperm;
+    RT_HD float4 item_a(uint32_t i) const { return m.ld4(32u * i); }
+    RT_HD float4 item_b(uint32_t i) const { return m.ld4(32u * i + 16u); }
+    RT_HD float4 node_q(uint32_t n, uint32_t q) const { return m.ld4(off_nodes + 64u * n + 16u * q); }
+    RT_HD uint2 frame(uint32_t f) const { return m.ld2(off_frames + 8u * f); }
+    RT_HD float4 op(uint32_t k) const { return m.ld4(off_ops + 16u * k); }
+    RT_HD float4 mat(uint32_t id, uint32_t half) const { return m.ld4(off_mats + 32u * id + 16u * half); }
+    RT_HD float4 tex(uint32_t id, uint32_t half) const { return m.ld4(off_tex + 32u * id + 16u * half); }
+    RT_HD float4 pvec(uint32_t i) const { return m.ld4(off_pvecs + 16u * i); }
+    RT_HD uint32_t pperm(uint32_t i) const { return m.ld1b(off_pperm + i); }
 };
 
-RT_HD Scene scene_views(const unsigned char* base, const KParams& P) {
-    Scene sc;
-    sc.items = reinterpret_cast<const float4*>(base);
-    sc.frames = reinterpret_cast<const uint2*>(base + P.off_frames);
-    sc.ops = reinterpret_cast<const float4*>(base + P.off_ops);
-    sc.mats = reinterpret_cast<const float4*>(base + P.off_mats);
-    sc.tex = reinterpret_cast<const float4*>(base + P.off_tex);
-    sc.pvecs = reinterpret_cast<const float4*>(base + P.off_pvecs);
-    sc.pperm = base + P.off_pperm;
+template <class Mem>
+RT_HD SceneT<Mem> scene_views(Mem m, const KParams& P) {
+    SceneT<Mem> sc;
+    sc.m = m;
+    sc.off_nodes = P.off_nodes; sc.off_frames = P.off_frames; sc.off_ops = P.off_ops; sc.off_mats = P.off_mats;
+    sc.off_tex = P.off_tex; sc.off_pvecs = P.off_pvecs; sc.off_pperm = P.off_pperm;
     return sc;
 }
 
@@ -140,13 +183,14 @@ RT_HD bool rect_hit_t(V3 o, V3 d, uint32_t axis, float4 ia, float4 ib, float t_l
 
 // Any primitive item against a ray in the frame just outside the item's own extra ops.
 // `skip_ops` = how many leading ops of the item's frame are already applied to (o, d).
-RT_HD bool prim_hit_t(const Scene& sc, float4 ia, float4 ib, V3 o, V3 d, float time, uint32_t skip_ops, float t_lo,
+template <class Mem>
+RT_HD bool prim_hit_t(const SceneT<Mem>& sc, float4 ia, float4 ib, V3 o, V3 d, float time, uint32_t skip_ops, float t_lo,
                       float t_hi, float& t_out) {
     const uint32_t kind = f2u(ia.w) & 15u;
     const uint32_t frame = f2u(ia.w) >> 4;
     const uint32_t flags = f2u(ib.w) >> 24;
-    const uint2 fr = sc.frames[frame];
-    for (uint32_t k = skip_ops; k < fr.y; ++k) apply_op_ray(sc.ops[fr.x + k], o, d, time);
+    const uint2 fr = sc.frame(frame);
+    for (uint32_t k = skip_ops; k < fr.y; ++k) apply_op_ray(sc.op(fr.x + k), o, d, time);
     if (kind == IT_SPHERE) {
         if (flags & FL_HAS_OFFSET) o = o - mk(ib.x, ib.y, ib.z);
         return sphere_hit_t(o, d, ia.x, t_lo, t_hi, t_out);
@@ -157,7 +201,8 @@ RT_HD bool prim_hit_t(const Scene& sc, float4 ia, float4 ib, V3 o, V3 d, float t
 // ------------------------------------------------------------------------------------------------
 // Textures (texture.rs) and Perlin noise (perlin.rs)
 // ------------------------------------------------------------------------------------------------
-RT_HD_NOINLINE float perlin_noise(const Scene& sc, V3 p) {  // perlin.rs:49-64 + trilinear_interp :31-47
+template <class Mem>
+RT_HD_NOINLINE float perlin_noise(const SceneT<Mem>& sc, V3 p) {  // perlin.rs:49-64 + trilinear_interp :31-47
     const V3 ijk = mk(floorf(p.x), floorf(p.y), floorf(p.z));
     const V3 uvw = p - ijk;
     const int bi = f2i_rz_sat(ijk.x), bj = f2i_rz_sat(ijk.y), bk = f2i_rz_sat(ijk.z);  // `as i32`
@@ -170,10 +215,10 @@ RT_HD_NOINLINE float perlin_noise(const Scene& sc, V3 p) {  // perlin.rs:49-64 +
         for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                const uint32_t ix = sc.pperm[(static_cast<uint32_t>(bi) + static_cast<uint32_t>(i)) & 255u];
-                const uint32_t iy = sc.pperm[256u + ((static_cast<uint32_t>(bj) + static_cast<uint32_t>(j)) & 255u)];
-                const uint32_t iz = sc.pperm[512u + ((static_cast<uint32_t>(bk) + static_cast<uint32_t>(k)) & 255u)];
-                const float4 cv = sc.pvecs[ix ^ iy ^ iz];
+                const uint32_t ix = sc.pperm((static_cast<uint32_t>(bi) + static_cast<uint32_t>(i)) & 255u);
+                const uint32_t iy = sc.pperm(256u + ((static_cast<uint32_t>(bj) + static_cast<uint32_t>(j)) & 255u));
+                const uint32_t iz = sc.pperm(512u + ((static_cast<uint32_t>(bk) + static_cast<uint32_t>(k)) & 255u));
+                const float4 cv = sc.pvec(ix ^ iy ^ iz);
                 const V3 ijkf = mk(static_cast<float>(i), static_cast<float>(j), static_cast<float>(k));
                 const float weight = dot(mk(cv.x, cv.y, cv.z), uvw - ijkf);
                 const V3 m = ijkf * uvw3 + (splat(1.f) - ijkf) * uvw3_inv;
@@ -182,7 +227,8 @@ RT_HD_NOINLINE float perlin_noise(const Scene& sc, V3 p) {  // perlin.rs:49-64 +
     return accum;
 }
 
-RT_HD_NOINLINE float perlin_turb(const Scene& sc, V3 p) {  // perlin.rs:66-75 with depth 7 (texture.rs:24)
+template <class Mem>
+RT_HD_NOINLINE float perlin_turb(const SceneT<Mem>& sc, V3 p) {  // perlin.rs:66-75 with depth 7 (texture.rs:24)
     float accum = 0.f, weight = 1.f;
     for (int i = 0; i < 7; ++i) {
         accum += weight * perlin_noise(sc, p);
@@ -192,12 +238,13 @@ RT_HD_NOINLINE float perlin_turb(const Scene& sc, V3 p) {  // perlin.rs:66-75 wi
     return fabsf(accum);
 }
 
-RT_HD_NOINLINE V3 texture_eval(const Scene& sc, uint32_t id, V3 p) {
+template <class Mem>
+RT_HD_NOINLINE V3 texture_eval(const SceneT<Mem>& sc, uint32_t id, V3 p) {
     for (;;) {
-        const float4 t0 = sc.tex[2 * id];
+        const float4 t0 = sc.tex(id, 0u);
         const uint32_t kind = f2u(t0.x);
         if (kind == TEX_CONSTANT) return mk(t0.y, t0.z, t0.w);            // texture.rs:8-10
-        const float4 t1 = sc.tex[2 * id + 1];
+        const float4 t1 = sc.tex(id, 1u);
         if (kind == TEX_PERLIN) return splat(perlin_turb(sc, t1.x * p));  // texture.rs:23-26
         const V3 q = 10.f * p;                                            // checker, texture.rs:12-21
         const float s = (sin_f32(q.x) * sin_f32(q.y)) * sin_f32(q.z);
@@ -206,7 +253,8 @@ RT_HD_NOINLINE V3 texture_eval(const Scene& sc, uint32_t id, V3 p) {
 }
 
 // Material's texture at p; constant textures were baked into the material record at scene upload.
-RT_HD V3 material_texture(const Scene& sc, float4 m0, float4 m1, V3 p) {
+template <class Mem>
+RT_HD V3 material_texture(const SceneT<Mem>& sc, float4 m0, float4 m1, V3 p) {
     const uint32_t texkind = (f2u(m0.x) >> 8) & 0xffu;
     if (texkind == TEX_CONSTANT) return mk(m1.x, m1.y, m1.z);
     return texture_eval(sc, f2u(m0.y), p);
@@ -268,11 +316,115 @@ RT_HD void generate_camera_ray(const KParams& P, PathState& st) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// World::hit_top over the threaded stream, in the reference's visiting order.  Returns the index
-// of the winning item (kNoHit if none) and its t.
+// Aabb::hit (aabb.rs:18-29) with the ray's 1/d hoisted (the same value at every node).  Returns
+// `end > start`; `start` is the entry parameter clamped to NEAR.
 // ------------------------------------------------------------------------------------------------
-template <bool kFrames>
-RT_HD uint32_t hit_top_stream(const Scene& sc, const PathState& st, float& best_t_out) {
+RT_HD bool slab_test(float4 mn, float4 mx, V3 fo, V3 inv, float t_end, float& start) {
+    const float ax = (mn.x - fo.x) * inv.x, ay = (mn.y - fo.y) * inv.y, az = (mn.z - fo.z) * inv.z;
+    const float bx = (mx.x - fo.x) * inv.x, by = (mx.y - fo.y) * inv.y, bz = (mx.z - fo.z) * inv.z;
+    const float n0x = inv.x < 0.f ? bx : ax, n1x = inv.x < 0.f ? ax : bx;
+    const float n0y = inv.y < 0.f ? by : ay, n1y = inv.y < 0.f ? ay : by;
+    const float n0z = inv.z < 0.f ? bz : az, n1z = inv.z < 0.f ? az : bz;
+    start = rt_max(kNear, rt_max(rt_max(n0x, n0y), n0z));
+    const float end = rt_min(t_end, rt_min(rt_min(n1x, n1y), n1z));
+    return end > start;
+}
+
+// The smallest float greater than a finite positive x.
+RT_HD float next_up_pos(float x) { return u2f(f2u(x) + 1u); }
+
+// ------------------------------------------------------------------------------------------------
+// A re-indexed Bvh subtree: SAH tree over the reference's leaf boxes, two child
+// boxes per node, nearer child first, per-lane stack of (link, entry t).  A leaf is a run of
+// primitive items tested in stream order with the reference's arithmetic.  The winner is the
+// smallest t, and among equal t the item that comes first in the reference's visiting order, which
+// is what `t < t_range.end` with a shrinking end gives in Bvh::hit (bvh.rs:94-106).
+// ------------------------------------------------------------------------------------------------
+template <class Mem>
+RT_HD void accel_traverse(const SceneT<Mem>& sc, uint32_t root, V3 fo, V3 fd, V3 inv, float time, uint32_t f_nops,
+                          float& best_t, uint32_t& best) {
+    uint32_t stk_link[kStackDepth];
+    float stk_t[kStackDepth];
+    int sp = 0;
+    uint32_t cur = root;
+    for (;;) {
+        while (!(cur & kLinkLeafBit)) {  // inner node: test both children
+            const float4 q0 = sc.node_q(cur, 0u), q1 = sc.node_q(cur, 1u);
+            const float4 q2 = sc.node_q(cur, 2u), q3 = sc.node_q(cur, 3u);
+            float s0, s1;
+            const bool h0 = slab_test(q0, q1, fo, inv, best_t, s0);
+            const uint32_t l0 = f2u(q0.w), l1 = f2u(q1.w);
+            const bool h1 = slab_test(q2, q3, fo, inv, best_t, s1) && l1 != kLinkNone;
+            if (h0 && h1) {
+                const bool first0 = s0 <= s1;
+                stk_link[sp] = first0 ? l1 : l0;
+                stk_t[sp] = first0 ? s1 : s0;
+                ++sp;
+                cur = first0 ? l0 : l1;
+            } else if (h0 || h1) {
+                cur = h0 ? l0 : l1;
+            } else {
+                cur = kLinkNone;
+                while (sp > 0) {  // pop, dropping entries the current best already beats (end > start)
+                    --sp;
+                    if (best_t > stk_t[sp]) { cur = stk_link[sp]; break; }
+                }
+                if (cur == kLinkNone) return;
+            }
+        }
+        {   // leaf: items [first, first + count)
+            const uint32_t first = cur & 0x00ffffffu, count = (cur >> 24) & 0x7fu;
+            for (uint32_t j = first; j < first + count; ++j) {
+                const float4 ia = sc.item_a(j), ib = sc.item_b(j);
+                const float t_hi = (best != kNoHit && j < best) ? next_up_pos(best_t) : best_t;
+                float t;
+                if (prim_hit_t(sc, ia, ib, fo, fd, time, f_nops, kNear, t_hi, t)) {
+                    best_t = t;
+                    best = j;
+                }
+            }
+        }
+        cur = kLinkNone;
+        while (sp > 0) {
+            --sp;
+            if (best_t > stk_t[sp]) { cur = stk_link[sp]; break; }
+        }
+        if (cur == kLinkNone) return;
+    }
+}
+
+// ConstantMedium::hit (object.rs:543-575); item i is the medium, item i+1 its boundary primitive.
+template <class Mem>
+RT_HD_NOINLINE void medium_hit(const SceneT<Mem>& sc, const PathState& st, uint32_t i, float4 ia, V3 fo, V3 fd,
+                               uint32_t f_nops, float& best_t, uint32_t& best) {
+    const uint2 fr = sc.frame(f2u(ia.w) >> 4);
+    V3 mo = fo, md = fd;
+    for (uint32_t k = f_nops; k < fr.y; ++k) apply_op_ray(sc.op(fr.x + k), mo, md, st.rtime);
+    const float4 ba = sc.item_a(i + 1u), bb = sc.item_b(i + 1u);
+    float t1, t2;
+    if (prim_hit_t(sc, ba, bb, mo, md, st.rtime, fr.y, kF32Min, kF32Max, t1) &&
+        prim_hit_t(sc, ba, bb, mo, md, st.rtime, fr.y, t1 + 0.0001f, kF32Max, t2)) {
+        t1 = rt_max(t1, kNear);
+        t2 = rt_min(t2, best_t);
+        if (!(t1 >= t2)) {
+            const float len = length(md);
+            const float distance_inside = (t2 - t1) * len;
+            const U4 mw = st.rng.block(st.bounce, PURPOSE_MEDIUM0 + f2u(ia.y), 0u);
+            const float hit_distance = -(1.f / ia.x) * ln_f32(unit_f32(mw.x));
+            if (hit_distance < distance_inside) {
+                best_t = t1 + hit_distance / len;
+                best = i;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// World::hit_top over the item stream, in the reference's visiting order (re-indexed subtrees are
+// order-free inside, see above).  Returns the index of the winning item (kNoHit if none) and its t.
+// ------------------------------------------------------------------------------------------------
+template <bool kFrames, class Mem>
+RT_HD uint32_t hit_top_stream(const SceneT<Mem>& sc, const PathState& st, float& best_t_out) {
     float best_t = kF32Max;
     uint32_t best = kNoHit;
     V3 fo = st.ro, fd = st.rd;  // ray in the current BBOX frame
@@ -280,54 +432,32 @@ RT_HD uint32_t hit_top_stream(const Scene& sc, const PathState& st, float& best_
     V3 inv = mk(1.f / fd.x, 1.f / fd.y, 1.f / fd.z);  // aabb.rs:19 (same value at every node)
     uint32_t i = 0u;
     for (;;) {
-        const float4 ia = sc.items[2u * i];
+        const float4 ia = sc.item_a(i);
         const uint32_t kind = f2u(ia.w) & 15u;
-        if (kind == IT_BBOX) {  // Aabb::hit  aabb.rs:18-29
-            const float4 ib = sc.items[2u * i + 1u];
-            const float ax = (ia.x - fo.x) * inv.x, ay = (ia.y - fo.y) * inv.y, az = (ia.z - fo.z) * inv.z;
-            const float bx = (ib.x - fo.x) * inv.x, by = (ib.y - fo.y) * inv.y, bz = (ib.z - fo.z) * inv.z;
-            const float n0x = inv.x < 0.f ? bx : ax, n1x = inv.x < 0.f ? ax : bx;
-            const float n0y = inv.y < 0.f ? by : ay, n1y = inv.y < 0.f ? ay : by;
-            const float n0z = inv.z < 0.f ? bz : az, n1z = inv.z < 0.f ? az : bz;
-            const float start = rt_max(kNear, rt_max(rt_max(n0x, n0y), n0z));
-            const float end = rt_min(best_t, rt_min(rt_min(n1x, n1y), n1z));
-            i = (end > start) ? i + 1u : (f2u(ia.w) >> 4);
+        if (kind == IT_ACCEL) {
+            accel_traverse(sc, f2u(ia.x), fo, fd, inv, st.rtime, f_nops, best_t, best);
+            i = f2u(ia.w) >> 4;
+        } else if (kind == IT_BBOX) {  // Aabb::hit  aabb.rs:18-29
+            const float4 ib = sc.item_b(i);
+            float start;
+            i = slab_test(ia, ib, fo, inv, best_t, start) ? i + 1u : (f2u(ia.w) >> 4);
         } else if (kind == IT_SPHERE || kind == IT_RECT) {
-            const float4 ib = sc.items[2u * i + 1u];
+            const float4 ib = sc.item_b(i);
             float t;
             if (prim_hit_t(sc, ia, ib, fo, fd, st.rtime, f_nops, kNear, best_t, t)) {
                 best_t = t;  // nearest = rec.t (lib.rs:42) / t_range.end = h.t (bvh.rs:98-100, object.rs:404-406)
                 best = i;
             }
             i += 1u;
-        } else if (kind == IT_MEDIUM) {  // ConstantMedium::hit  object.rs:543-575
-            const uint2 fr = sc.frames[f2u(ia.w) >> 4];
-            V3 mo = fo, md = fd;
-            for (uint32_t k = f_nops; k < fr.y; ++k) apply_op_ray(sc.ops[fr.x + k], mo, md, st.rtime);
-            const float4 ba = sc.items[2u * i + 2u], bb = sc.items[2u * i + 3u];
-            float t1, t2;
-            if (prim_hit_t(sc, ba, bb, mo, md, st.rtime, fr.y, kF32Min, kF32Max, t1) &&
-                prim_hit_t(sc, ba, bb, mo, md, st.rtime, fr.y, t1 + 0.0001f, kF32Max, t2)) {
-                t1 = rt_max(t1, kNear);
-                t2 = rt_min(t2, best_t);
-                if (!(t1 >= t2)) {
-                    const float len = length(md);
-                    const float distance_inside = (t2 - t1) * len;
-                    const U4 mw = st.rng.block(st.bounce, PURPOSE_MEDIUM0 + f2u(ia.y), 0u);
-                    const float hit_distance = -(1.f / ia.x) * ln_f32(unit_f32(mw.x));
-                    if (hit_distance < distance_inside) {
-                        best_t = t1 + hit_distance / len;
-                        best = i;
-                    }
-                }
-            }
+        } else if (kind == IT_MEDIUM) {
+            medium_hit(sc, st, i, ia, fo, fd, f_nops, best_t, best);
             i += 2u;
         } else if (kind == IT_SET_FRAME) {
             if (kFrames) {
-                const uint2 fr = sc.frames[f2u(ia.w) >> 4];
+                const uint2 fr = sc.frame(f2u(ia.w) >> 4);
                 fo = st.ro;
                 fd = st.rd;
-                for (uint32_t k = 0; k < fr.y; ++k) apply_op_ray(sc.ops[fr.x + k], fo, fd, st.rtime);
+                for (uint32_t k = 0; k < fr.y; ++k) apply_op_ray(sc.op(fr.x + k), fo, fd, st.rtime);
                 f_nops = fr.y;
                 inv = mk(1.f / fd.x, 1.f / fd.y, 1.f / fd.z);
             }
@@ -344,7 +474,8 @@ RT_HD uint32_t hit_top_stream(const Scene& sc, const PathState& st, float& best_
 // The body of color()'s loop after hit_top (lib.rs:73-98).  Returns true when the path is finished
 // and `result` holds what color() returns; otherwise st carries the scattered ray.
 // ------------------------------------------------------------------------------------------------
-RT_HD bool shade_and_scatter(const Scene& sc, const KParams& P, PathState& st, uint32_t best, float best_t, V3& result) {
+template <class Mem>
+RT_HD bool shade_and_scatter(const SceneT<Mem>& sc, const KParams& P, PathState& st, uint32_t best, float best_t, V3& result) {
     result = splat(0.f);
     if (best == kNoHit) {  // lib.rs:100, or the book-1 sky (rtiow_b200.h RTIOW_BG_SKY_GRADIENT)
         if (P.bg_kind == 1u) {
@@ -355,12 +486,12 @@ RT_HD bool shade_and_scatter(const Scene& sc, const KParams& P, PathState& st, u
         return true;
     }
     // ---- rebuild the HitRecord of the winning item (object.rs:61-71) --------------------------
-    const float4 ia = sc.items[2u * best], ib = sc.items[2u * best + 1u];
+    const float4 ia = sc.item_a(best), ib = sc.item_b(best);
     const uint32_t kind = f2u(ia.w) & 15u;
     const uint32_t flags = f2u(ib.w) >> 24;
-    const uint2 fr = sc.frames[f2u(ia.w) >> 4];
+    const uint2 fr = sc.frame(f2u(ia.w) >> 4);
     V3 lo = st.ro, ld = st.rd;
-    for (uint32_t k = 0; k < fr.y; ++k) apply_op_ray(sc.ops[fr.x + k], lo, ld, st.rtime);
+    for (uint32_t k = 0; k < fr.y; ++k) apply_op_ray(sc.op(fr.x + k), lo, ld, st.rtime);
     V3 p, n;
     if (kind == IT_SPHERE) {
         if (flags & FL_HAS_OFFSET) lo = lo - mk(ib.x, ib.y, ib.z);
@@ -377,10 +508,10 @@ RT_HD bool shade_and_scatter(const Scene& sc, const KParams& P, PathState& st, u
         p = lo + best_t * ld;
         n = mk(1.f, 0.f, 0.f);
     }
-    for (uint32_t k = fr.y; k > 0u; --k) apply_op_hit(sc.ops[fr.x + k - 1u], p, n);
+    for (uint32_t k = fr.y; k > 0u; --k) apply_op_hit(sc.op(fr.x + k - 1u), p, n);
 
     const uint32_t mat_id = f2u(ib.w) & 0x00ffffffu;
-    const float4 m0 = sc.mats[2u * mat_id], m1 = sc.mats[2u * mat_id + 1u];
+    const float4 m0 = sc.mat(mat_id, 0u), m1 = sc.mat(mat_id, 1u);
     const uint32_t mkind = f2u(m0.x) & 0xffu;
     const V3 rd = st.rd;
     bool done = false;

@@ -14,6 +14,8 @@
 //  * per-sample radiance goes to a staging buffer with one 16-byte store; a second kernel folds
 //    the samples of each pixel left to right exactly like `.sum()` (vec3.rs:195-203).
 #pragma once
+#include <type_traits>
+
 #include "path_logic.cuh"
 
 namespace rtiow {
@@ -59,14 +61,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
 
-    const unsigned char* base;
+    using Mem = typename std::conditional<kSmem, MemShared, MemGlobal>::type;
+    Mem mem;
     if constexpr (kSmem) {
         stage_scene_tma(smem_raw, P.blob, P.blob_bytes, &mbar);
-        base = smem_raw;
+        mem.base = smem_u32(smem_raw);
     } else {
-        base = P.blob;
+        mem.base = P.blob;
     }
-    const Scene sc = scene_views(base, P);
+    const SceneT<Mem> sc = scene_views(mem, P);
 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;

@@ -16,22 +16,23 @@ def lib():
     if _lib is None:
         src = os.path.join(_HERE, "kernel_host_harness.cpp")
         deps = [src] + [os.path.join(_HERE, "..", "rtiow-rust_b200", "csrc", d, f) for d, f in
-                        (("device", "path_logic.cuh"), ("device", "rt_math.cuh"), ("abi", "scene_blob.hpp"))]
+                        (("device", "path_logic.cuh"), ("device", "rt_math.cuh"), ("abi", "scene_blob.hpp"), ("abi", "accel_build.hpp"))]
         if not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps):
             os.makedirs(os.path.dirname(_SO), exist_ok=True)
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", _SO, src])
         _lib = C.CDLL(_SO)
         _lib.harness_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
-                                        C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+                                        C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     return _lib
 
 
-def render(world, camera, nx, ny, ns, seed=0xDEADBEEF, rows=None, want_samples=False):
+def render(world, camera, nx, ny, ns, seed=0xDEADBEEF, rows=None, want_samples=False, accel=True, layout=None):
     r0, r1 = rows if rows is not None else (0, ny)
     img = np.zeros((r1 - r0, nx, 3), np.float32)
     smp = np.zeros((r1 - r0, nx, ns, 4), np.float32) if want_samples else None
     rc = lib().harness_render(C.cast(world.desc, C.c_void_p), C.byref(camera.rec), nx, ny, ns, seed, r0, r1,
-                              img.ctypes.data, smp.ctypes.data if want_samples else None)
+                              img.ctypes.data, smp.ctypes.data if want_samples else None, int(accel),
+                              layout.ctypes.data if layout is not None else None)
     if rc:
         raise RuntimeError(f"harness_render failed: {rc}")
     return img, smp

@@ -12,19 +12,21 @@
 #include "../rtiow-rust_b200/csrc/abi/scene_blob.hpp"
 #include "../rtiow-rust_b200/csrc/device/path_logic.cuh"
 
+// accel != 0: the re-indexed (SAH, ordered) traversal the device uses; 0: the plain reference-order stream.
 extern "C" int harness_render(const rtiow_scene_desc_t* desc, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny,
                               uint32_t ns, uint64_t seed, uint32_t row_begin, uint32_t row_end, float* out_rgb,
-                              float* out_samples) {
+                              float* out_samples, int accel, uint32_t* layout_out) {
     using namespace rtiow;
     bool has_frames = false, uses_perlin = false;
     std::string msg;
     if (int rc = validate_desc(desc, &has_frames, &uses_perlin, &msg)) return rc;
     BlobLayout lay{};
-    const std::vector<unsigned char> blob = build_blob(desc, uses_perlin, &lay);
+    const std::vector<unsigned char> blob = build_blob(desc, uses_perlin, &lay, accel != 0);
+    if (layout_out) { layout_out[0] = lay.n_items; layout_out[1] = lay.n_nodes; layout_out[2] = lay.n_accel; layout_out[3] = lay.accel_depth; }
     KParams P{};
     P.blob = blob.data();
     P.blob_bytes = static_cast<uint32_t>(blob.size());
-    P.off_frames = lay.off_frames; P.off_ops = lay.off_ops; P.off_mats = lay.off_mats; P.off_tex = lay.off_tex;
+    P.off_nodes = lay.off_nodes; P.off_frames = lay.off_frames; P.off_ops = lay.off_ops; P.off_mats = lay.off_mats; P.off_tex = lay.off_tex;
     P.off_pvecs = lay.off_pvecs; P.off_pperm = lay.off_pperm;
     std::memcpy(P.cam, cam, sizeof(float) * 21);
     P.nx = nx; P.ny = ny; P.row_begin = row_begin; P.n_rows = row_end - row_begin;
@@ -34,7 +36,7 @@ extern "C" int harness_render(const rtiow_scene_desc_t* desc, const rtiow_camera
     P.bg_kind = desc->background_kind;
     std::memcpy(P.bg0, desc->background_c0, 12);
     std::memcpy(P.bg1, desc->background_c1, 12);
-    const Scene sc = scene_views(blob.data(), P);
+    const SceneT<MemPtr> sc = scene_views(MemPtr{blob.data()}, P);
     for (uint32_t pix = 0; pix < P.npix; ++pix) {
         float acc[3] = {0.f, 0.f, 0.f};
         for (uint32_t s = 0; s < ns; ++s) {

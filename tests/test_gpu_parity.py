@@ -101,6 +101,24 @@ def test_execution_shape_does_not_change_results():
     assert world.stats()["scene_in_smem"] == 0
     world.set_tuning(ctas_per_sm=1)
     assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, ref)
+    world.set_tuning()
+    assert world.stats()["accel_subtrees"] > 0
+    world.set_traversal(1)                               # the reference's own visiting order instead of the re-indexed tree
+    assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, ref)
+    assert world.stats()["accel_subtrees"] == 0
+
+
+@pytest.mark.parametrize("name,bvh,size", [("book1", True, (240, 160, 12)), ("final", False, (96, 96, 12)),
+                                           ("final", True, (96, 96, 12)), ("simple_light", True, (96, 64, 8))])
+def test_traversal_modes_agree_per_sample(name, bvh, size):
+    """Re-indexed (SAH, near child first) vs reference-order traversal: every per-sample radiance and
+    segment count identical (ties resolved to the earlier item in the reference's order)."""
+    nx, ny, ns = size
+    world, cam = R.build_scene(name, nx, ny, use_bvh=bvh)
+    a = api.render_samples(nx, ny, ns, cam, world, seed=99)
+    world.set_traversal(1)
+    b = api.render_samples(nx, ny, ns, cam, world, seed=99)
+    assert n_diff(a, b) == 0
 
 
 def test_determinism_and_seed():

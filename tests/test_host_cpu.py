@@ -169,21 +169,46 @@ def test_flattened_stream_logic_matches_golden():
     """The kernel's per-path code, compiled for the host, over the product's flattened scenes."""
     for key, name, nx, ny, ns, bvh, want, segs in golden_cases():
         world, cam = R.build_scene(name, nx, ny, use_bvh=bvh)
-        got, smp = H.render(world, cam, nx, ny, ns, want_samples=True)
-        assert n_diff(got, want) == 0, key
-        assert int(smp[..., 3].sum()) == segs, key
+        for accel in (True, False):      # the re-indexed Bvh traversal and the reference-order stream
+            got, smp = H.render(world, cam, nx, ny, ns, want_samples=True, accel=accel)
+            assert n_diff(got, want) == 0, (key, accel)
+            assert int(smp[..., 3].sum()) == segs, (key, accel)
 
 
 @pytest.mark.parametrize("name,bvh", [("book1", True), ("cornell", False), ("final", False), ("final", True),
                                       ("kitchen_sink", True), ("kitchen_sink", False), ("volume_test", False)])
-def test_flattened_stream_logic_matches_oracle_per_sample(oracle, name, bvh):
+@pytest.mark.parametrize("accel", [True, False])
+def test_flattened_stream_logic_matches_oracle_per_sample(oracle, name, bvh, accel):
     nx, ny, ns = 40, 30, 5
     world, cam = R.build_scene(name, nx, ny, use_bvh=bvh)
-    _, smp = H.render(world, cam, nx, ny, ns, seed=12345, want_samples=True)
+    _, smp = H.render(world, cam, nx, ny, ns, seed=12345, want_samples=True, accel=accel)
     _, osmp, cnt = oracle.Scene(name, nx, ny, top_level_bvh=bvh).render(ns, seed=12345, nthreads=4, want_samples=True,
                                                                        want_counters=True)
     assert n_diff(smp[..., :3], osmp) == 0
     assert int(smp[..., 3].sum()) == cnt["segments"]
+
+
+def test_reindexed_subtrees_layout():
+    """Which Bvh subtrees the device library re-indexes: pure box/primitive subtrees
+    become one ACCEL item + an (n_leaves - 1)-node tree; media, frame switches and list elements stay
+    on the reference-order stream."""
+    def layout(name, bvh, accel=True):
+        world, cam = R.build_scene(name, 8, 8, use_bvh=bvh)
+        lay = np.zeros(4, np.uint32)
+        H.render(world, cam, 8, 8, 1, accel=accel, layout=lay)
+        return world.counts(), dict(items=int(lay[0]), nodes=int(lay[1]), accels=int(lay[2]), depth=int(lay[3]))
+    c, l = layout("book1", True)
+    assert l["accels"] == 1 and l["nodes"] == c["spheres"] - 1            # one leaf per sphere
+    assert l["items"] == c["spheres"] + 2 and l["depth"] <= 30            # ACCEL + spheres + END: no BBOX items left
+    c, l = layout("book1", True, accel=False)
+    assert l == dict(items=c["items"], nodes=0, accels=0, depth=0)        # the stream as flattened
+    c, l = layout("book1", False)
+    assert l["accels"] == 0                                               # a plain list has no boxes to re-index
+    c, l = layout("final", False)
+    assert l["accels"] == 2 and l["nodes"] == (400 - 1) + (1000 - 1)      # the box floor and the sphere cube
+    assert l["items"] == c["items"] - c["bbox"] + 2                       # every BBOX item replaced by 2 ACCEL items
+    c, l = layout("final", True)                                          # top-level Bvh holds media -> stays threaded,
+    assert l["accels"] >= 2 and l["items"] < c["items"]                   # its pure subtrees are still re-indexed
 
 
 def test_print_ppm_formatting(tmp_path, oracle):
