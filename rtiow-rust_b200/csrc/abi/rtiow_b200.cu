@@ -96,6 +96,8 @@ Variant pick_threads(uint32_t threads) {
     switch (threads) {
         case 128: return {rtiow::render_kernel<S, F, 128, 1>, 128};
         case 512: return {rtiow::render_kernel<S, F, 512, 1>, 512};
+        case 768: return {rtiow::render_kernel<S, F, 768, 1>, 768};
+        case 1024: return {rtiow::render_kernel<S, F, 1024, 1>, 1024};
         default: return {rtiow::render_kernel<S, F, 256, 1>, 256};
     }
 }
@@ -301,8 +303,8 @@ void rtiow_b200_scene_destroy(rtiow_scene_t* s) {
 int rtiow_b200_set_tuning(rtiow_scene_t* s, uint32_t cta_threads, uint32_t ctas_per_sm, uint32_t staging_mib, int force_global) {
     if (!s) return set_err(RTIOW_ERR_INVALID_ARG, "null scene");
     if (cta_threads) {
-        if (cta_threads != 128 && cta_threads != 256 && cta_threads != 512)
-            return set_err(RTIOW_ERR_INVALID_ARG, "cta_threads must be 128, 256 or 512");
+        if (cta_threads != 128 && cta_threads != 256 && cta_threads != 512 && cta_threads != 768 && cta_threads != 1024)
+            return set_err(RTIOW_ERR_INVALID_ARG, "cta_threads must be 128, 256, 512, 768 or 1024");
         s->cta_threads = cta_threads;
     }
     s->ctas_per_sm = ctas_per_sm;

@@ -151,6 +151,23 @@ RT_HD void apply_op_hit(const float4 op, V3& p, V3& n) {
     }                                      // LinearMove: result returned unmodified (object.rs:504-511)
 }
 
+// The wrapper chain of a frame, applied out of line: wrapped primitives are rare on the hot scenes
+// and the Scale/RotateY arithmetic is bulky (IEEE divisions), so one copy of each loop keeps the
+// megakernel's instruction footprint small.  ops [first, first + n) given as a byte offset.
+struct Ray6 {
+    V3 o, d;
+};
+template <class Mem>
+RT_HD_NOINLINE Ray6 frame_ops_ray(Mem m, uint32_t first_off, uint32_t n, V3 o, V3 d, float time) {
+    for (uint32_t k = 0; k < n; ++k) apply_op_ray(m.ld4(first_off + 16u * k), o, d, time);  // outermost first
+    return Ray6{o, d};
+}
+template <class Mem>
+RT_HD_NOINLINE Ray6 frame_ops_hit(Mem m, uint32_t first_off, uint32_t n, V3 p, V3 nrm) {
+    for (uint32_t k = n; k > 0u; --k) apply_op_hit(m.ld4(first_off + 16u * (k - 1u)), p, nrm);  // innermost first
+    return Ray6{p, nrm};
+}
+
 // Sphere::hit (object.rs:82-111) on a ray already in the sphere's frame.
 RT_HD bool sphere_hit_t(V3 o, V3 d, float radius, float t_lo, float t_hi, float& t_out) {
     const float a = dot(d, d);
@@ -181,16 +198,21 @@ RT_HD bool rect_hit_t(V3 o, V3 d, uint32_t axis, float4 ia, float4 ib, float t_l
     return true;
 }
 
-// Any primitive item against a ray in the frame just outside the item's own extra ops.
-// `skip_ops` = how many leading ops of the item's frame are already applied to (o, d).
+// Any primitive item against a ray (o, d) that is already in frame `cur_frame` (whose chain has
+// `cur_nops` ops, a prefix of the item's own chain): the item's remaining wrappers are applied
+// first, exactly like the nested Object::hit calls.
 template <class Mem>
-RT_HD bool prim_hit_t(const SceneT<Mem>& sc, float4 ia, float4 ib, V3 o, V3 d, float time, uint32_t skip_ops, float t_lo,
-                      float t_hi, float& t_out) {
+RT_HD bool prim_hit_t(const SceneT<Mem>& sc, float4 ia, float4 ib, V3 o, V3 d, float time, uint32_t cur_frame,
+                      uint32_t cur_nops, float t_lo, float t_hi, float& t_out) {
     const uint32_t kind = f2u(ia.w) & 15u;
     const uint32_t frame = f2u(ia.w) >> 4;
     const uint32_t flags = f2u(ib.w) >> 24;
-    const uint2 fr = sc.frame(frame);
-    for (uint32_t k = skip_ops; k < fr.y; ++k) apply_op_ray(sc.op(fr.x + k), o, d, time);
+    if (frame != cur_frame) {
+        const uint2 fr = sc.frame(frame);
+        const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * (fr.x + cur_nops), fr.y - cur_nops, o, d, time);
+        o = r.o;
+        d = r.d;
+    }
     if (kind == IT_SPHERE) {
         if (flags & FL_HAS_OFFSET) o = o - mk(ib.x, ib.y, ib.z);
         return sphere_hit_t(o, d, ia.x, t_lo, t_hi, t_out);
@@ -341,8 +363,8 @@ RT_HD float next_up_pos(float x) { return u2f(f2u(x) + 1u); }
 // is what `t < t_range.end` with a shrinking end gives in Bvh::hit (bvh.rs:94-106).
 // ------------------------------------------------------------------------------------------------
 template <class Mem>
-RT_HD void accel_traverse(const SceneT<Mem>& sc, uint32_t root, V3 fo, V3 fd, V3 inv, float time, uint32_t f_nops,
-                          float& best_t, uint32_t& best) {
+RT_HD void accel_traverse(const SceneT<Mem>& sc, uint32_t root, V3 fo, V3 fd, V3 inv, float time, uint32_t f_id,
+                          uint32_t f_nops, float& best_t, uint32_t& best) {
     uint32_t stk_link[kStackDepth];
     float stk_t[kStackDepth];
     int sp = 0;
@@ -378,7 +400,7 @@ RT_HD void accel_traverse(const SceneT<Mem>& sc, uint32_t root, V3 fo, V3 fd, V3
                 const float4 ia = sc.item_a(j), ib = sc.item_b(j);
                 const float t_hi = (best != kNoHit && j < best) ? next_up_pos(best_t) : best_t;
                 float t;
-                if (prim_hit_t(sc, ia, ib, fo, fd, time, f_nops, kNear, t_hi, t)) {
+                if (prim_hit_t(sc, ia, ib, fo, fd, time, f_id, f_nops, kNear, t_hi, t)) {
                     best_t = t;
                     best = j;
                 }
@@ -394,22 +416,34 @@ RT_HD void accel_traverse(const SceneT<Mem>& sc, uint32_t root, V3 fo, V3 fd, V3
 }
 
 // ConstantMedium::hit (object.rs:543-575); item i is the medium, item i+1 its boundary primitive.
+struct BestHit {
+    float t;
+    uint32_t item;
+};
 template <class Mem>
-RT_HD_NOINLINE void medium_hit(const SceneT<Mem>& sc, const PathState& st, uint32_t i, float4 ia, V3 fo, V3 fd,
-                               uint32_t f_nops, float& best_t, uint32_t& best) {
-    const uint2 fr = sc.frame(f2u(ia.w) >> 4);
+RT_HD_NOINLINE BestHit medium_hit(const SceneT<Mem> sc, Rng rng, uint32_t bounce, float time, uint32_t i, V3 fo, V3 fd,
+                                  uint32_t f_id, uint32_t f_nops, float best_t, uint32_t best) {
+    const float4 ia = sc.item_a(i);
+    const uint32_t mframe = f2u(ia.w) >> 4;
     V3 mo = fo, md = fd;
-    for (uint32_t k = f_nops; k < fr.y; ++k) apply_op_ray(sc.op(fr.x + k), mo, md, st.rtime);
+    uint32_t m_nops = f_nops;
+    if (mframe != f_id) {
+        const uint2 fr = sc.frame(mframe);
+        const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * (fr.x + f_nops), fr.y - f_nops, mo, md, time);
+        mo = r.o;
+        md = r.d;
+        m_nops = fr.y;
+    }
     const float4 ba = sc.item_a(i + 1u), bb = sc.item_b(i + 1u);
     float t1, t2;
-    if (prim_hit_t(sc, ba, bb, mo, md, st.rtime, fr.y, kF32Min, kF32Max, t1) &&
-        prim_hit_t(sc, ba, bb, mo, md, st.rtime, fr.y, t1 + 0.0001f, kF32Max, t2)) {
+    if (prim_hit_t(sc, ba, bb, mo, md, time, mframe, m_nops, kF32Min, kF32Max, t1) &&
+        prim_hit_t(sc, ba, bb, mo, md, time, mframe, m_nops, t1 + 0.0001f, kF32Max, t2)) {
         t1 = rt_max(t1, kNear);
         t2 = rt_min(t2, best_t);
         if (!(t1 >= t2)) {
             const float len = length(md);
             const float distance_inside = (t2 - t1) * len;
-            const U4 mw = st.rng.block(st.bounce, PURPOSE_MEDIUM0 + f2u(ia.y), 0u);
+            const U4 mw = rng.block(bounce, PURPOSE_MEDIUM0 + f2u(ia.y), 0u);
             const float hit_distance = -(1.f / ia.x) * ln_f32(unit_f32(mw.x));
             if (hit_distance < distance_inside) {
                 best_t = t1 + hit_distance / len;
@@ -417,6 +451,7 @@ RT_HD_NOINLINE void medium_hit(const SceneT<Mem>& sc, const PathState& st, uint3
             }
         }
     }
+    return BestHit{best_t, best};
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -428,14 +463,17 @@ RT_HD uint32_t hit_top_stream(const SceneT<Mem>& sc, const PathState& st, float&
     float best_t = kF32Max;
     uint32_t best = kNoHit;
     V3 fo = st.ro, fd = st.rd;  // ray in the current BBOX frame
-    uint32_t f_nops = 0u;
+    uint32_t f_id = 0u, f_nops = 0u;
     V3 inv = mk(1.f / fd.x, 1.f / fd.y, 1.f / fd.z);  // aabb.rs:19 (same value at every node)
+    // the last wrapped primitive's frame: the six rects of a rotated prism share one chain
+    uint32_t pf_id = 0u;
+    V3 po = fo, pd = fd;
     uint32_t i = 0u;
     for (;;) {
         const float4 ia = sc.item_a(i);
         const uint32_t kind = f2u(ia.w) & 15u;
         if (kind == IT_ACCEL) {
-            accel_traverse(sc, f2u(ia.x), fo, fd, inv, st.rtime, f_nops, best_t, best);
+            accel_traverse(sc, f2u(ia.x), fo, fd, inv, st.rtime, f_id, f_nops, best_t, best);
             i = f2u(ia.w) >> 4;
         } else if (kind == IT_BBOX) {  // Aabb::hit  aabb.rs:18-29
             const float4 ib = sc.item_b(i);
@@ -443,23 +481,38 @@ RT_HD uint32_t hit_top_stream(const SceneT<Mem>& sc, const PathState& st, float&
             i = slab_test(ia, ib, fo, inv, best_t, start) ? i + 1u : (f2u(ia.w) >> 4);
         } else if (kind == IT_SPHERE || kind == IT_RECT) {
             const float4 ib = sc.item_b(i);
+            const uint32_t frame = f2u(ia.w) >> 4;
+            if (frame != f_id && frame != pf_id) {
+                const uint2 fr = sc.frame(frame);
+                const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * (fr.x + f_nops), fr.y - f_nops, fo, fd, st.rtime);
+                po = r.o;
+                pd = r.d;
+                pf_id = frame;
+            }
+            const bool own = frame != f_id;
             float t;
-            if (prim_hit_t(sc, ia, ib, fo, fd, st.rtime, f_nops, kNear, best_t, t)) {
+            if (prim_hit_t(sc, ia, ib, own ? po : fo, own ? pd : fd, st.rtime, frame, 0u, kNear, best_t, t)) {
                 best_t = t;  // nearest = rec.t (lib.rs:42) / t_range.end = h.t (bvh.rs:98-100, object.rs:404-406)
                 best = i;
             }
             i += 1u;
         } else if (kind == IT_MEDIUM) {
-            medium_hit(sc, st, i, ia, fo, fd, f_nops, best_t, best);
+            const BestHit h = medium_hit(sc, st.rng, st.bounce, st.rtime, i, fo, fd, f_id, f_nops, best_t, best);
+            best_t = h.t;
+            best = h.item;
             i += 2u;
         } else if (kind == IT_SET_FRAME) {
             if (kFrames) {
-                const uint2 fr = sc.frame(f2u(ia.w) >> 4);
-                fo = st.ro;
-                fd = st.rd;
-                for (uint32_t k = 0; k < fr.y; ++k) apply_op_ray(sc.op(fr.x + k), fo, fd, st.rtime);
+                f_id = f2u(ia.w) >> 4;
+                const uint2 fr = sc.frame(f_id);
+                const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * fr.x, fr.y, st.ro, st.rd, st.rtime);
+                fo = r.o;
+                fd = r.d;
                 f_nops = fr.y;
                 inv = mk(1.f / fd.x, 1.f / fd.y, 1.f / fd.z);
+                pf_id = f_id;
+                po = fo;
+                pd = fd;
             }
             i += 1u;
         } else {
@@ -489,9 +542,16 @@ RT_HD bool shade_and_scatter(const SceneT<Mem>& sc, const KParams& P, PathState&
     const float4 ia = sc.item_a(best), ib = sc.item_b(best);
     const uint32_t kind = f2u(ia.w) & 15u;
     const uint32_t flags = f2u(ib.w) >> 24;
-    const uint2 fr = sc.frame(f2u(ia.w) >> 4);
+    const uint32_t frame = f2u(ia.w) >> 4;
+    uint2 fr;
+    fr.x = 0u; fr.y = 0u;
     V3 lo = st.ro, ld = st.rd;
-    for (uint32_t k = 0; k < fr.y; ++k) apply_op_ray(sc.op(fr.x + k), lo, ld, st.rtime);
+    if (frame != 0u) {
+        fr = sc.frame(frame);
+        const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * fr.x, fr.y, lo, ld, st.rtime);
+        lo = r.o;
+        ld = r.d;
+    }
     V3 p, n;
     if (kind == IT_SPHERE) {
         if (flags & FL_HAS_OFFSET) lo = lo - mk(ib.x, ib.y, ib.z);
@@ -508,7 +568,11 @@ RT_HD bool shade_and_scatter(const SceneT<Mem>& sc, const KParams& P, PathState&
         p = lo + best_t * ld;
         n = mk(1.f, 0.f, 0.f);
     }
-    for (uint32_t k = fr.y; k > 0u; --k) apply_op_hit(sc.op(fr.x + k - 1u), p, n);
+    if (fr.y != 0u) {
+        const Ray6 r = frame_ops_hit(sc.m, sc.off_ops + 16u * fr.x, fr.y, p, n);
+        p = r.o;
+        n = r.d;
+    }
 
     const uint32_t mat_id = f2u(ib.w) & 0x00ffffffu;
     const float4 m0 = sc.mat(mat_id, 0u), m1 = sc.mat(mat_id, 1u);

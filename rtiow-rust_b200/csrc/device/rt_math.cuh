@@ -10,7 +10,7 @@
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
 #define RT_HD __host__ __device__ __forceinline__
-#define RT_HD_NOINLINE __host__ __device__
+#define RT_HD_NOINLINE __host__ __device__ __noinline__
 #else
 // Host-only build of the same per-path code, used by tests/kernel_host_harness.cpp to check the
 // flattened-stream logic against the oracle without a GPU.  Not part of any shipped library.
