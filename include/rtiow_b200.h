@@ -184,6 +184,9 @@ int rtiow_b200_scene_validate(const rtiow_scene_desc_t* desc);
 /* Validates `desc`, copies it to `device` (CUDA ordinal) and returns a handle. */
 int rtiow_b200_scene_create(const rtiow_scene_desc_t* desc, int device, rtiow_scene_t** out);
 void rtiow_b200_scene_destroy(rtiow_scene_t* scene);
+/* Destroyed scenes leave their device work buffers in a small per-device cache for the next
+ * scene_create; this frees them. */
+void rtiow_b200_release_cached_memory(void);
 
 /* par_cast (src/lib.rs:363-376) with an explicit seed: out_rgb receives ny*nx*3 floats, row 0 =
  * TOP scanline (lib.rs:326-330), linear (pre-gamma), already divided by ns (lib.rs:374) — i.e.
@@ -214,7 +217,7 @@ int rtiow_b200_ppm_quantise(rtiow_scene_t* scene, const float* linear, size_t n,
 /* Synchronises the scene's device and reports the last render. */
 int rtiow_b200_get_stats(rtiow_scene_t* scene, rtiow_stats_t* out);
 
-/* Tuning knobs (0 = keep default): threads per CTA, CTAs per SM, staging budget in MiB,
+/* Tuning knobs (0 = default / automatic): threads per CTA (128..1024), CTAs per SM, staging budget in MiB,
  * force_global != 0 keeps the scene in global memory even if it fits shared memory. */
 int rtiow_b200_set_tuning(rtiow_scene_t* scene, uint32_t cta_threads, uint32_t ctas_per_sm, uint32_t staging_mib,
                           int force_global);

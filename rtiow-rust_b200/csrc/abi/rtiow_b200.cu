@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -48,6 +49,114 @@ struct DevBuf {
     }
 };
 
+// Device buffers, stream and events of one render in flight.  A scene owns one for its lifetime;
+// destroyed scenes hand theirs to a small per-device cache so that create/render/destroy cycles
+// (one per frame in a host application) do not pay cudaMalloc/cudaFree of the sample staging buffer.
+struct Workspace {
+    int device = 0;
+    DevBuf staging, accum, out, samples;
+    unsigned int* d_counter = nullptr;
+    unsigned long long* d_segs = nullptr;
+    cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> events;  // [start, trace_end, fold_end] per pass
+    // two pinned bounce buffers: device -> pinned -> caller's pageable memory, pipelined
+    static constexpr size_t kBounce = 4u << 20;
+    void* pinned[2] = {nullptr, nullptr};
+    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+
+    cudaError_t init(int dev) {
+        device = dev;
+        cudaError_t e;
+        if ((e = cudaMalloc(reinterpret_cast<void**>(&d_counter), sizeof(unsigned int))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(reinterpret_cast<void**>(&d_segs), sizeof(unsigned long long))) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        return cudaSuccess;
+    }
+    void destroy() {
+        cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        staging.release(); accum.release(); out.release(); samples.release();
+        if (d_counter) cudaFree(d_counter);
+        if (d_segs) cudaFree(d_segs);
+        for (cudaEvent_t ev : events) cudaEventDestroy(ev);
+        for (int i = 0; i < 2; ++i) {
+            if (pinned[i]) cudaFreeHost(pinned[i]);
+            if (pin_ev[i]) cudaEventDestroy(pin_ev[i]);
+        }
+        if (stream) cudaStreamDestroy(stream);
+    }
+    // Device -> caller's (pageable) host memory, ordered after everything enqueued on `stream`;
+    // returns when the data is in `dst`.
+    cudaError_t copy_to_host(void* dst, const void* src, size_t bytes) {
+        cudaError_t e;
+        if (bytes <= (256u << 10)) {
+            if ((e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+            return cudaStreamSynchronize(stream);
+        }
+        for (int i = 0; i < 2; ++i) {
+            if (!pinned[i] && (e = cudaMallocHost(&pinned[i], kBounce)) != cudaSuccess) return e;
+            if (!pin_ev[i] && (e = cudaEventCreateWithFlags(&pin_ev[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+        }
+        const size_t n = (bytes + kBounce - 1) / kBounce;
+        auto size_of = [&](size_t i) { return std::min(kBounce, bytes - i * kBounce); };
+        auto drain = [&](size_t i) -> cudaError_t {
+            cudaError_t de = cudaEventSynchronize(pin_ev[i & 1]);
+            if (de == cudaSuccess) std::memcpy(static_cast<char*>(dst) + i * kBounce, pinned[i & 1], size_of(i));
+            return de;
+        };
+        for (size_t i = 0; i < n; ++i) {
+            if (i >= 2 && (e = drain(i - 2)) != cudaSuccess) return e;
+            if ((e = cudaMemcpyAsync(pinned[i & 1], static_cast<const char*>(src) + i * kBounce, size_of(i), cudaMemcpyDeviceToHost,
+                                     stream)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(pin_ev[i & 1], stream)) != cudaSuccess) return e;
+        }
+        for (size_t i = n >= 2 ? n - 2 : 0; i < n; ++i)
+            if ((e = drain(i)) != cudaSuccess) return e;
+        return cudaSuccess;
+    }
+};
+
+std::mutex g_ws_mutex;
+std::vector<Workspace*> g_ws_cache;
+constexpr size_t kWsCachePerDevice = 2;
+
+Workspace* ws_acquire(int device, cudaError_t* err) {
+    {
+        std::lock_guard<std::mutex> lock(g_ws_mutex);
+        for (size_t i = 0; i < g_ws_cache.size(); ++i)
+            if (g_ws_cache[i]->device == device) {
+                Workspace* w = g_ws_cache[i];
+                g_ws_cache.erase(g_ws_cache.begin() + static_cast<std::ptrdiff_t>(i));
+                return w;
+            }
+    }
+    auto w = new Workspace();
+    *err = w->init(device);
+    if (*err != cudaSuccess) {
+        w->destroy();
+        delete w;
+        return nullptr;
+    }
+    return w;
+}
+
+void ws_release(Workspace* w) {
+    if (!w) return;
+    cudaSetDevice(w->device);
+    cudaStreamSynchronize(w->stream);
+    {
+        std::lock_guard<std::mutex> lock(g_ws_mutex);
+        size_t same = 0;
+        for (Workspace* c : g_ws_cache) same += c->device == w->device;
+        if (same < kWsCachePerDevice) {
+            g_ws_cache.push_back(w);
+            return;
+        }
+    }
+    w->destroy();
+    delete w;
+}
+
 }  // namespace
 
 struct rtiow_scene {
@@ -56,6 +165,7 @@ struct rtiow_scene {
     int max_smem_optin = 0;
     // [0] = re-indexed Bvh subtrees (default), [1] = the plain reference-order stream
     struct Blob {
+        std::vector<unsigned char> host;  // uploaded on first use
         unsigned char* d = nullptr;
         uint32_t bytes = 0;
         rtiow::BlobLayout lay{};
@@ -65,15 +175,11 @@ struct rtiow_scene {
     uint32_t bg_kind = 0;
     float bg0[3] = {0, 0, 0}, bg1[3] = {0, 0, 0};
 
-    DevBuf staging, accum, out, samples;
-    unsigned int* d_counter = nullptr;
-    unsigned long long* d_segs = nullptr;
-    cudaStream_t own_stream = nullptr;
-    std::vector<cudaEvent_t> events;  // [start, trace_end, fold_end] per pass
+    Workspace* ws = nullptr;
     uint32_t events_used = 0;
 
     // tuning
-    uint32_t cta_threads = 256, ctas_per_sm = 0, staging_mib = 2048;
+    uint32_t cta_threads = 0, ctas_per_sm = 0, staging_mib = 2048, sample_chunk = 0;
     bool force_global = false;
 
     // last render
@@ -95,10 +201,10 @@ template <bool S, bool F>
 Variant pick_threads(uint32_t threads) {
     switch (threads) {
         case 128: return {rtiow::render_kernel<S, F, 128, 1>, 128};
+        case 256: return {rtiow::render_kernel<S, F, 256, 1>, 256};
         case 512: return {rtiow::render_kernel<S, F, 512, 1>, 512};
-        case 768: return {rtiow::render_kernel<S, F, 768, 1>, 768};
         case 1024: return {rtiow::render_kernel<S, F, 1024, 1>, 1024};
-        default: return {rtiow::render_kernel<S, F, 256, 1>, 256};
+        default: return {rtiow::render_kernel<S, F, 768, 1>, 768};
     }
 }
 
@@ -108,11 +214,18 @@ Variant pick_variant(bool smem, bool frames, uint32_t threads) {
 }
 
 int ensure_events(rtiow_scene* s, uint32_t n) {
-    while (s->events.size() < n) {
+    while (s->ws->events.size() < n) {
         cudaEvent_t e;
         CK(cudaEventCreate(&e));
-        s->events.push_back(e);
+        s->ws->events.push_back(e);
     }
+    return RTIOW_OK;
+}
+
+int ensure_uploaded(rtiow_scene* s, rtiow_scene::Blob& B) {
+    if (B.d) return RTIOW_OK;
+    CK(cudaMalloc(reinterpret_cast<void**>(&B.d), B.bytes));
+    CK(cudaMemcpy(B.d, B.host.data(), B.bytes, cudaMemcpyHostToDevice));
     return RTIOW_OK;
 }
 
@@ -137,13 +250,17 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     const uint64_t budget = static_cast<uint64_t>(s->staging_mib) << 20;
     uint32_t s_pass = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(ns, budget / (npix64 * 16))));
     const uint32_t n_pass = (ns + s_pass - 1) / s_pass;
-    CK(s->staging.reserve(npix64 * s_pass * 16));
-    CK(s->accum.reserve(npix64 * 16));
+    Workspace& W = *s->ws;
+    CK(W.staging.reserve(npix64 * s_pass * 16));
+    CK(W.accum.reserve(npix64 * 16));
 
-    const rtiow_scene::Blob& B = s->blobs[s->traversal];
+    rtiow_scene::Blob& B = s->blobs[s->traversal];
+    if (int rc = ensure_uploaded(s, B)) return rc;
     const bool fits = B.bytes + 1024u <= static_cast<uint32_t>(s->max_smem_optin);
     const bool smem = fits && !s->force_global;
-    const Variant var = pick_variant(smem, s->has_frames, s->cta_threads);
+    // 0 = automatic: 768 threads (80 registers) per CTA, one CTA per SM; scenes with wrapper frames keep 512
+    const uint32_t threads = s->cta_threads ? s->cta_threads : (s->has_frames ? 512u : 768u);
+    const Variant var = pick_variant(smem, s->has_frames, threads);
     const size_t dyn_smem = smem ? B.bytes : 0;
     CK(cudaFuncSetAttribute(var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem)));
     int occ = 0;
@@ -168,22 +285,30 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     P.key0 = static_cast<uint32_t>(seed); P.key1 = static_cast<uint32_t>(seed >> 32);
     P.bg_kind = s->bg_kind;
     std::memcpy(P.bg0, s->bg0, 12); std::memcpy(P.bg1, s->bg1, 12);
-    P.staging = static_cast<float4*>(s->staging.p);
-    P.work_counter = s->d_counter;
+    P.staging = static_cast<float4*>(W.staging.p);
+    P.work_counter = W.d_counter;
 
+    const uint32_t chunk_pref = s->sample_chunk ? s->sample_chunk : 8u;
     if (int rc = ensure_events(s, 1 + 2 * n_pass)) return rc;
     s->events_used = 0;
-    CK(cudaMemsetAsync(s->d_segs, 0, sizeof(unsigned long long), stream));
-    CK(cudaEventRecord(s->events[s->events_used++], stream));
+    CK(cudaMemsetAsync(W.d_segs, 0, sizeof(unsigned long long), stream));
+    CK(cudaEventRecord(W.events[s->events_used++], stream));
     uint32_t launches = 0;
     for (uint32_t pass = 0; pass < n_pass; ++pass) {
         P.s_begin = pass * s_pass;
         P.s_count = std::min(s_pass, ns - P.s_begin);
-        CK(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned int), stream));
+        P.s_chunk = std::min(chunk_pref, P.s_count);
+        P.n_chunks = (P.s_count + P.s_chunk - 1) / P.s_chunk;
+        if (static_cast<uint64_t>(n_groups) * P.n_chunks >= (1ull << 32)) {  // keep the unit counter in 32 bits
+            P.s_chunk = P.s_count;
+            P.n_chunks = 1;
+        }
+        P.n_units = n_groups * P.n_chunks;
+        CK(cudaMemsetAsync(W.d_counter, 0, sizeof(unsigned int), stream));
         var.fn<<<grid, var.threads, dyn_smem, stream>>>(P);
         CK(cudaGetLastError());
         ++launches;
-        CK(cudaEventRecord(s->events[s->events_used++], stream));
+        CK(cudaEventRecord(W.events[s->events_used++], stream));
         if (d_samples) {
             const uint64_t n = npix64 * P.s_count;
             rtiow::export_samples_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
@@ -193,12 +318,12 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
         }
         if (d_out) {
             rtiow::fold_kernel<<<(npix + 255u) / 256u, 256, 0, stream>>>(
-                P.staging, static_cast<float4*>(s->accum.p), d_out, npix, P.s_count, pass == 0, pass + 1 == n_pass,
-                static_cast<float>(ns), s->d_segs);
+                P.staging, static_cast<float4*>(W.accum.p), d_out, npix, P.s_count, pass == 0, pass + 1 == n_pass,
+                static_cast<float>(ns), W.d_segs);
             CK(cudaGetLastError());
             ++launches;
         }
-        CK(cudaEventRecord(s->events[s->events_used++], stream));
+        CK(cudaEventRecord(W.events[s->events_used++], stream));
     }
     s->stats = rtiow_stats_t{};
     s->stats.samples = npix64 * ns;
@@ -268,35 +393,44 @@ int rtiow_b200_scene_create(const rtiow_scene_desc_t* d, int device, rtiow_scene
     // ---- build the device blobs: items | accel nodes | frames | ops | materials | textures | perlin
     for (int v = 0; v < 2; ++v) {
         rtiow_scene::Blob& B = s->blobs[v];
-        const std::vector<unsigned char> blob = rtiow::build_blob(d, uses_perlin, &B.lay, v == 0);
-        B.bytes = static_cast<uint32_t>(blob.size());
-        if ((e = cudaMalloc(reinterpret_cast<void**>(&B.d), B.bytes)) != cudaSuccess) return fail(e, "cudaMalloc(blob)");
-        if ((e = cudaMemcpy(B.d, blob.data(), B.bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e, "cudaMemcpy(blob)");
+        B.host = rtiow::build_blob(d, uses_perlin, &B.lay, v == 0);
+        B.bytes = static_cast<uint32_t>(B.host.size());
     }
-    if ((e = cudaMalloc(reinterpret_cast<void**>(&s->d_counter), sizeof(unsigned int))) != cudaSuccess) return fail(e, "cudaMalloc");
-    if ((e = cudaMalloc(reinterpret_cast<void**>(&s->d_segs), sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc");
-    if ((e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    s->ws = ws_acquire(device, &e);
+    if (!s->ws) return fail(e, "workspace");
 
     if (const char* env = std::getenv("RTIOW_B200_CTA_THREADS")) s->cta_threads = static_cast<uint32_t>(std::atoi(env));
     if (const char* env = std::getenv("RTIOW_B200_CTAS_PER_SM")) s->ctas_per_sm = static_cast<uint32_t>(std::atoi(env));
     if (const char* env = std::getenv("RTIOW_B200_STAGING_MIB")) s->staging_mib = static_cast<uint32_t>(std::atoi(env));
     if (const char* env = std::getenv("RTIOW_B200_FORCE_GLOBAL")) s->force_global = std::atoi(env) != 0;
     if (const char* env = std::getenv("RTIOW_B200_TRAVERSAL")) s->traversal = std::atoi(env) != 0 ? 1 : 0;
+    if (const char* env = std::getenv("RTIOW_B200_SAMPLE_CHUNK")) s->sample_chunk = static_cast<uint32_t>(std::max(0, std::atoi(env)));
+    if (int rc = ensure_uploaded(s, s->blobs[s->traversal])) {
+        rtiow_b200_scene_destroy(s);
+        return rc;
+    }
     *out = s;
     return RTIOW_OK;
+}
+
+void rtiow_b200_release_cached_memory(void) {
+    std::vector<Workspace*> drop;
+    {
+        std::lock_guard<std::mutex> lock(g_ws_mutex);
+        drop.swap(g_ws_cache);
+    }
+    for (Workspace* w : drop) {
+        w->destroy();
+        delete w;
+    }
 }
 
 void rtiow_b200_scene_destroy(rtiow_scene_t* s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    cudaDeviceSynchronize();
+    ws_release(s->ws);  // synchronises the scene's stream first
     for (auto& B : s->blobs)
         if (B.d) cudaFree(B.d);
-    if (s->d_counter) cudaFree(s->d_counter);
-    if (s->d_segs) cudaFree(s->d_segs);
-    s->staging.release(); s->accum.release(); s->out.release(); s->samples.release();
-    for (cudaEvent_t ev : s->events) cudaEventDestroy(ev);
-    if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
 }
 
@@ -305,8 +439,8 @@ int rtiow_b200_set_tuning(rtiow_scene_t* s, uint32_t cta_threads, uint32_t ctas_
     if (cta_threads) {
         if (cta_threads != 128 && cta_threads != 256 && cta_threads != 512 && cta_threads != 768 && cta_threads != 1024)
             return set_err(RTIOW_ERR_INVALID_ARG, "cta_threads must be 128, 256, 512, 768 or 1024");
-        s->cta_threads = cta_threads;
     }
+    s->cta_threads = cta_threads;
     s->ctas_per_sm = ctas_per_sm;
     if (staging_mib) s->staging_mib = staging_mib;
     s->force_global = force_global != 0;
@@ -332,10 +466,10 @@ int rtiow_b200_render_rows(rtiow_scene_t* s, const rtiow_camera_t* cam, uint32_t
     if (int rc = check_render_args(s, cam, nx, ny, ns, r0, r1, out_rows)) return rc;
     CK(cudaSetDevice(s->device));
     const size_t bytes = static_cast<size_t>(r1 - r0) * nx * 3 * sizeof(float);
-    CK(s->out.reserve(bytes));
-    if (int rc = enqueue_render(s, cam, nx, ny, ns, seed, r0, r1, static_cast<float*>(s->out.p), nullptr, s->own_stream)) return rc;
-    CK(cudaMemcpyAsync(out_rows, s->out.p, bytes, cudaMemcpyDeviceToHost, s->own_stream));
-    CK(cudaStreamSynchronize(s->own_stream));
+    Workspace& W = *s->ws;
+    CK(W.out.reserve(bytes));
+    if (int rc = enqueue_render(s, cam, nx, ny, ns, seed, r0, r1, static_cast<float*>(W.out.p), nullptr, W.stream)) return rc;
+    CK(W.copy_to_host(out_rows, W.out.p, bytes));
     return RTIOW_OK;
 }
 
@@ -349,24 +483,24 @@ int rtiow_b200_render_samples(rtiow_scene_t* s, const rtiow_camera_t* cam, uint3
     if (int rc = check_render_args(s, cam, nx, ny, ns, r0, r1, out_samples)) return rc;
     CK(cudaSetDevice(s->device));
     const size_t bytes = static_cast<size_t>(r1 - r0) * nx * ns * 4 * sizeof(float);
-    CK(s->samples.reserve(bytes));
-    if (int rc = enqueue_render(s, cam, nx, ny, ns, seed, r0, r1, nullptr, static_cast<float4*>(s->samples.p), s->own_stream)) return rc;
-    CK(cudaMemcpyAsync(out_samples, s->samples.p, bytes, cudaMemcpyDeviceToHost, s->own_stream));
-    CK(cudaStreamSynchronize(s->own_stream));
+    Workspace& W = *s->ws;
+    CK(W.samples.reserve(bytes));
+    if (int rc = enqueue_render(s, cam, nx, ny, ns, seed, r0, r1, nullptr, static_cast<float4*>(W.samples.p), W.stream)) return rc;
+    CK(W.copy_to_host(out_samples, W.samples.p, bytes));
     return RTIOW_OK;
 }
 
 int rtiow_b200_ppm_quantise(rtiow_scene_t* s, const float* linear, size_t n, uint8_t* out) {
     if (!s || !linear || !out || n == 0) return set_err(RTIOW_ERR_INVALID_ARG, "null argument");
     CK(cudaSetDevice(s->device));
-    CK(s->out.reserve(n * sizeof(float)));
-    CK(s->samples.reserve(n));
-    CK(cudaMemcpyAsync(s->out.p, linear, n * sizeof(float), cudaMemcpyHostToDevice, s->own_stream));
-    rtiow::ppm_quantise_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s->own_stream>>>(
-        static_cast<const float*>(s->out.p), static_cast<unsigned char*>(s->samples.p), n);
+    Workspace& W = *s->ws;
+    CK(W.out.reserve(n * sizeof(float)));
+    CK(W.samples.reserve(n));
+    CK(cudaMemcpyAsync(W.out.p, linear, n * sizeof(float), cudaMemcpyHostToDevice, W.stream));
+    rtiow::ppm_quantise_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, W.stream>>>(
+        static_cast<const float*>(W.out.p), static_cast<unsigned char*>(W.samples.p), n);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out, s->samples.p, n, cudaMemcpyDeviceToHost, s->own_stream));
-    CK(cudaStreamSynchronize(s->own_stream));
+    CK(W.copy_to_host(out, W.samples.p, n));
     return RTIOW_OK;
 }
 
@@ -377,15 +511,15 @@ int rtiow_b200_get_stats(rtiow_scene_t* s, rtiow_stats_t* out) {
     double trace = 0, fold = 0;
     for (uint32_t i = 0; i + 2 < s->events_used; i += 2) {  // [start, (trace_end, fold_end) per pass]
         float a = 0, b = 0;
-        CK(cudaEventElapsedTime(&a, s->events[i], s->events[i + 1]));
-        CK(cudaEventElapsedTime(&b, s->events[i + 1], s->events[i + 2]));
+        CK(cudaEventElapsedTime(&a, s->ws->events[i], s->ws->events[i + 1]));
+        CK(cudaEventElapsedTime(&b, s->ws->events[i + 1], s->ws->events[i + 2]));
         trace += a;
         fold += b;
     }
     s->stats.trace_ms = trace;
     s->stats.reduce_ms = fold;
     unsigned long long segs = 0;
-    CK(cudaMemcpy(&segs, s->d_segs, sizeof(segs), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&segs, s->ws->d_segs, sizeof(segs), cudaMemcpyDeviceToHost));
     s->stats.segments = segs;
     *out = s->stats;
     return RTIOW_OK;

@@ -33,6 +33,7 @@ struct KParams {
     uint32_t nx, ny, row_begin, n_rows;
     uint32_t s_begin, s_count;  // samples [s_begin, s_begin + s_count) of every pixel in this pass
     uint32_t npix, n_groups;
+    uint32_t s_chunk, n_chunks, n_units;  // work unit = s_chunk samples of one 32-pixel group
     uint32_t key0, key1;
     uint32_t bg_kind;
     float bg0[3], bg1[3];
@@ -356,6 +357,59 @@ RT_HD bool slab_test(float4 mn, float4 mx, V3 fo, V3 inv, float t_end, float& st
 RT_HD float next_up_pos(float x) { return u2f(f2u(x) + 1u); }
 
 // ------------------------------------------------------------------------------------------------
+// Traversal state of one lane for one hit_top call.  hit_top is written as resumable steps
+// (stream step / node step / leaf step) so that the megakernel can interleave the steps of its 32
+// lanes any way it likes (render_kernel.cuh); run back to back they are World::hit_top.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kStreamEnd = 0xffffffffu;
+
+struct Trav {
+    uint32_t i;        // next stream item to interpret; kStreamEnd once the stream is finished
+    uint32_t cur;      // link being visited inside a re-indexed subtree; kLinkNone outside
+    int sp;            // stack height
+    float best_t;      // t_range.end so far
+    uint32_t best;     // winning item so far
+    V3 fo, fd, inv;    // the ray in the current BBOX frame and its 1/d (aabb.rs:19)
+    uint32_t f_id, f_nops;
+};
+// The per-lane stack of (link, entry t) lives apart from Trav: a dynamically indexed array sits in
+// local memory, and must not drag the scalars above there with it.
+struct TravStack {
+    uint32_t link[kStackDepth];
+    float t[kStackDepth];
+};
+
+RT_HD bool trav_in_node(const Trav& tr) { return tr.cur < kLinkNone; }
+RT_HD bool trav_in_leaf(const Trav& tr) { return (tr.cur & kLinkLeafBit) != 0u; }
+RT_HD bool trav_done(const Trav& tr) { return tr.cur == kLinkNone && tr.i == kStreamEnd; }
+
+RT_HD void trav_begin(const PathState& st, Trav& tr) {
+    tr.i = 0u;
+    tr.cur = kLinkNone;
+    tr.sp = 0;
+    tr.best_t = kF32Max;
+    tr.best = kNoHit;
+    tr.fo = st.ro;
+    tr.fd = st.rd;
+    tr.inv = mk(1.f / st.rd.x, 1.f / st.rd.y, 1.f / st.rd.z);
+    tr.f_id = 0u;
+    tr.f_nops = 0u;
+}
+
+// Pop the next link worth visiting: entries the current best already beats are dropped (their box
+// test `end > start` would fail now, aabb.rs:27-28).
+RT_HD void trav_pop(Trav& tr, const TravStack& stk) {
+    tr.cur = kLinkNone;
+    while (tr.sp > 0) {
+        --tr.sp;
+        if (tr.best_t > stk.t[tr.sp]) {
+            tr.cur = stk.link[tr.sp];
+            break;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // A re-indexed Bvh subtree: SAH tree over the reference's leaf boxes, two child
 // boxes per node, nearer child first, per-lane stack of (link, entry t).  A leaf is a run of
 // primitive items tested in stream order with the reference's arithmetic.  The winner is the
@@ -363,56 +417,44 @@ RT_HD float next_up_pos(float x) { return u2f(f2u(x) + 1u); }
 // is what `t < t_range.end` with a shrinking end gives in Bvh::hit (bvh.rs:94-106).
 // ------------------------------------------------------------------------------------------------
 template <class Mem>
-RT_HD void accel_traverse(const SceneT<Mem>& sc, uint32_t root, V3 fo, V3 fd, V3 inv, float time, uint32_t f_id,
-                          uint32_t f_nops, float& best_t, uint32_t& best) {
-    uint32_t stk_link[kStackDepth];
-    float stk_t[kStackDepth];
-    int sp = 0;
-    uint32_t cur = root;
-    for (;;) {
-        while (!(cur & kLinkLeafBit)) {  // inner node: test both children
-            const float4 q0 = sc.node_q(cur, 0u), q1 = sc.node_q(cur, 1u);
-            const float4 q2 = sc.node_q(cur, 2u), q3 = sc.node_q(cur, 3u);
-            float s0, s1;
-            const bool h0 = slab_test(q0, q1, fo, inv, best_t, s0);
-            const uint32_t l0 = f2u(q0.w), l1 = f2u(q1.w);
-            const bool h1 = slab_test(q2, q3, fo, inv, best_t, s1) && l1 != kLinkNone;
-            if (h0 && h1) {
-                const bool first0 = s0 <= s1;
-                stk_link[sp] = first0 ? l1 : l0;
-                stk_t[sp] = first0 ? s1 : s0;
-                ++sp;
-                cur = first0 ? l0 : l1;
-            } else if (h0 || h1) {
-                cur = h0 ? l0 : l1;
-            } else {
-                cur = kLinkNone;
-                while (sp > 0) {  // pop, dropping entries the current best already beats (end > start)
-                    --sp;
-                    if (best_t > stk_t[sp]) { cur = stk_link[sp]; break; }
-                }
-                if (cur == kLinkNone) return;
-            }
-        }
-        {   // leaf: items [first, first + count)
-            const uint32_t first = cur & 0x00ffffffu, count = (cur >> 24) & 0x7fu;
-            for (uint32_t j = first; j < first + count; ++j) {
-                const float4 ia = sc.item_a(j), ib = sc.item_b(j);
-                const float t_hi = (best != kNoHit && j < best) ? next_up_pos(best_t) : best_t;
-                float t;
-                if (prim_hit_t(sc, ia, ib, fo, fd, time, f_id, f_nops, kNear, t_hi, t)) {
-                    best_t = t;
-                    best = j;
-                }
-            }
-        }
-        cur = kLinkNone;
-        while (sp > 0) {
-            --sp;
-            if (best_t > stk_t[sp]) { cur = stk_link[sp]; break; }
-        }
-        if (cur == kLinkNone) return;
+RT_HD void trav_node_step(const SceneT<Mem>& sc, Trav& tr, TravStack& stk) {  // requires trav_in_node(tr)
+    const uint32_t n = tr.cur;
+    const float4 q0 = sc.node_q(n, 0u), q1 = sc.node_q(n, 1u);
+    const float4 q2 = sc.node_q(n, 2u), q3 = sc.node_q(n, 3u);
+    float s0, s1;
+    const bool h0 = slab_test(q0, q1, tr.fo, tr.inv, tr.best_t, s0);
+    const uint32_t l0 = f2u(q0.w), l1 = f2u(q1.w);
+    const bool h1 = slab_test(q2, q3, tr.fo, tr.inv, tr.best_t, s1) && l1 != kLinkNone;
+    if (h0 && h1) {
+        const bool first0 = s0 <= s1;
+        stk.link[tr.sp] = first0 ? l1 : l0;
+        stk.t[tr.sp] = first0 ? s1 : s0;
+        ++tr.sp;
+        tr.cur = first0 ? l0 : l1;
+    } else if (h0 || h1) {
+        tr.cur = h0 ? l0 : l1;
+    } else {
+        trav_pop(tr, stk);
     }
+}
+
+template <class Mem>
+RT_HD void trav_leaf_test(const SceneT<Mem>& sc, float time, Trav& tr, uint32_t link) {
+    const uint32_t first = link & 0x00ffffffu, count = (link >> 24) & 0x7fu;
+    for (uint32_t j = first; j < first + count; ++j) {
+        const float4 ia = sc.item_a(j), ib = sc.item_b(j);
+        const float t_hi = (tr.best != kNoHit && j < tr.best) ? next_up_pos(tr.best_t) : tr.best_t;
+        float t;
+        if (prim_hit_t(sc, ia, ib, tr.fo, tr.fd, time, tr.f_id, tr.f_nops, kNear, t_hi, t)) {
+            tr.best_t = t;
+            tr.best = j;
+        }
+    }
+}
+template <class Mem>
+RT_HD void trav_leaf_step(const SceneT<Mem>& sc, float time, Trav& tr, const TravStack& stk) {  // requires trav_in_leaf(tr)
+    trav_leaf_test(sc, time, tr, tr.cur);
+    trav_pop(tr, stk);
 }
 
 // ConstantMedium::hit (object.rs:543-575); item i is the medium, item i+1 its boundary primitive.
@@ -456,71 +498,91 @@ RT_HD_NOINLINE BestHit medium_hit(const SceneT<Mem> sc, Rng rng, uint32_t bounce
 
 // ------------------------------------------------------------------------------------------------
 // World::hit_top over the item stream, in the reference's visiting order (re-indexed subtrees are
-// order-free inside, see above).  Returns the index of the winning item (kNoHit if none) and its t.
+// order-free inside, see above).
 // ------------------------------------------------------------------------------------------------
+// Interprets stream items from tr.i until a re-indexed subtree starts (tr.cur = its root) or the
+// stream ends (tr.i = kStreamEnd).
 template <bool kFrames, class Mem>
-RT_HD uint32_t hit_top_stream(const SceneT<Mem>& sc, const PathState& st, float& best_t_out) {
-    float best_t = kF32Max;
-    uint32_t best = kNoHit;
-    V3 fo = st.ro, fd = st.rd;  // ray in the current BBOX frame
-    uint32_t f_id = 0u, f_nops = 0u;
-    V3 inv = mk(1.f / fd.x, 1.f / fd.y, 1.f / fd.z);  // aabb.rs:19 (same value at every node)
+RT_HD void trav_stream(const SceneT<Mem>& sc, const PathState& st, Trav& tr) {
     // the last wrapped primitive's frame: the six rects of a rotated prism share one chain
-    uint32_t pf_id = 0u;
-    V3 po = fo, pd = fd;
-    uint32_t i = 0u;
+    uint32_t pf_id = tr.f_id;
+    V3 po = tr.fo, pd = tr.fd;
+    uint32_t i = tr.i;
     for (;;) {
         const float4 ia = sc.item_a(i);
         const uint32_t kind = f2u(ia.w) & 15u;
         if (kind == IT_ACCEL) {
-            accel_traverse(sc, f2u(ia.x), fo, fd, inv, st.rtime, f_id, f_nops, best_t, best);
+            tr.cur = f2u(ia.x);
+            tr.sp = 0;
             i = f2u(ia.w) >> 4;
+            break;
         } else if (kind == IT_BBOX) {  // Aabb::hit  aabb.rs:18-29
             const float4 ib = sc.item_b(i);
             float start;
-            i = slab_test(ia, ib, fo, inv, best_t, start) ? i + 1u : (f2u(ia.w) >> 4);
+            i = slab_test(ia, ib, tr.fo, tr.inv, tr.best_t, start) ? i + 1u : (f2u(ia.w) >> 4);
         } else if (kind == IT_SPHERE || kind == IT_RECT) {
             const float4 ib = sc.item_b(i);
             const uint32_t frame = f2u(ia.w) >> 4;
-            if (frame != f_id && frame != pf_id) {
+            if (frame != tr.f_id && frame != pf_id) {
                 const uint2 fr = sc.frame(frame);
-                const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * (fr.x + f_nops), fr.y - f_nops, fo, fd, st.rtime);
+                const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * (fr.x + tr.f_nops), fr.y - tr.f_nops, tr.fo, tr.fd, st.rtime);
                 po = r.o;
                 pd = r.d;
                 pf_id = frame;
             }
-            const bool own = frame != f_id;
+            const bool own = frame != tr.f_id;
             float t;
-            if (prim_hit_t(sc, ia, ib, own ? po : fo, own ? pd : fd, st.rtime, frame, 0u, kNear, best_t, t)) {
-                best_t = t;  // nearest = rec.t (lib.rs:42) / t_range.end = h.t (bvh.rs:98-100, object.rs:404-406)
-                best = i;
+            if (prim_hit_t(sc, ia, ib, own ? po : tr.fo, own ? pd : tr.fd, st.rtime, frame, 0u, kNear, tr.best_t, t)) {
+                tr.best_t = t;  // nearest = rec.t (lib.rs:42) / t_range.end = h.t (bvh.rs:98-100, object.rs:404-406)
+                tr.best = i;
             }
             i += 1u;
         } else if (kind == IT_MEDIUM) {
-            const BestHit h = medium_hit(sc, st.rng, st.bounce, st.rtime, i, fo, fd, f_id, f_nops, best_t, best);
-            best_t = h.t;
-            best = h.item;
+            const BestHit h = medium_hit(sc, st.rng, st.bounce, st.rtime, i, tr.fo, tr.fd, tr.f_id, tr.f_nops, tr.best_t, tr.best);
+            tr.best_t = h.t;
+            tr.best = h.item;
             i += 2u;
         } else if (kind == IT_SET_FRAME) {
             if (kFrames) {
-                f_id = f2u(ia.w) >> 4;
-                const uint2 fr = sc.frame(f_id);
+                tr.f_id = f2u(ia.w) >> 4;
+                const uint2 fr = sc.frame(tr.f_id);
                 const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * fr.x, fr.y, st.ro, st.rd, st.rtime);
-                fo = r.o;
-                fd = r.d;
-                f_nops = fr.y;
-                inv = mk(1.f / fd.x, 1.f / fd.y, 1.f / fd.z);
-                pf_id = f_id;
-                po = fo;
-                pd = fd;
+                tr.fo = r.o;
+                tr.fd = r.d;
+                tr.f_nops = fr.y;
+                tr.inv = mk(1.f / tr.fd.x, 1.f / tr.fd.y, 1.f / tr.fd.z);
+                pf_id = tr.f_id;
+                po = tr.fo;
+                pd = tr.fd;
             }
             i += 1u;
         } else {
-            break;  // IT_END
+            i = kStreamEnd;  // IT_END
+            break;
         }
     }
-    best_t_out = best_t;
-    return best;
+    tr.i = i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// World::hit_top: the steps above run back to back for one ray.  Returns the index of the winning
+// item (kNoHit if none) and its t.
+// ------------------------------------------------------------------------------------------------
+template <bool kFrames, class Mem>
+RT_HD uint32_t hit_top_stream(const SceneT<Mem>& sc, const PathState& st, float& best_t_out) {
+    Trav tr;
+    TravStack stk;
+    trav_begin(st, tr);
+    for (;;) {
+        trav_stream<kFrames>(sc, st, tr);
+        while (tr.cur != kLinkNone) {  // "while-while": lanes stay together in the cheap node loop
+            while (trav_in_node(tr)) trav_node_step(sc, tr, stk);
+            if (trav_in_leaf(tr)) trav_leaf_step(sc, st.rtime, tr, stk);
+        }
+        if (tr.i == kStreamEnd) break;
+    }
+    best_t_out = tr.best_t;
+    return tr.best;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -8,7 +8,8 @@
 //    into shared memory with TMA bulk copies (cp.async.bulk + mbarrier) when it fits;
 //  * one warp lane = one pixel-sample in flight.  A warp owns a group of 32 neighbouring pixels
 //    and hands their samples to lanes as they fall idle (__ballot_sync + prefix popcount), so
-//    lanes stay busy although path lengths differ wildly; groups come from a global counter;
+//    lanes stay busy although path lengths differ wildly; (group, sample chunk) units come from
+//    a global counter;
 //  * the object tree is a stack-less "threaded" stream in the reference's visiting order, so a
 //    lane's traversal state is just a cursor and the nearest hit so far;
 //  * per-sample radiance goes to a staging buffer with one 16-byte store; a second kernel folds
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     // ---- warp-uniform job pool: the samples of one 32-pixel group ----------------------------
-    uint32_t pool_base = 0, pool_valid = 32, pool_next = 0, pool_end = 0;
+    uint32_t pool_base = 0, pool_valid = 32, pool_next = 0, pool_end = 0, pool_s0 = 0;
     bool exhausted = false;
 
     // ---- per-lane path state ------------------------------------------------------------------
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
                 const uint32_t avail = pool_end - pool_next;
                 if (need && !fresh && my_rank < avail) {
                     const uint32_t job = pool_next + my_rank;
-                    st.samp = P.s_begin + job / pool_valid;
+                    st.samp = P.s_begin + pool_s0 + job / pool_valid;
                     st.pix = pool_base + job % pool_valid;
                     fresh = true;
                 }
@@ -107,14 +108,18 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
                 remaining -= taken;
                 my_rank -= taken;  // only meaningful for lanes still waiting
                 if (remaining == 0u) break;
-                uint32_t g = 0;
-                if (lane == 0) g = atomicAdd(P.work_counter, 1u);
-                g = __shfl_sync(0xffffffffu, g, 0);
-                if (g >= P.n_groups) { exhausted = true; break; }
+                uint32_t u = 0;
+                if (lane == 0) u = atomicAdd(P.work_counter, 1u);
+                u = __shfl_sync(0xffffffffu, u, 0);
+                if (u >= P.n_units) { exhausted = true; break; }
+                // unit u = samples [c * s_chunk, ...) of pixel group g; small units keep the tail short
+                const uint32_t g = u / P.n_chunks, c = u - g * P.n_chunks;
                 pool_base = g * 32u;
                 pool_valid = P.npix - pool_base < 32u ? P.npix - pool_base : 32u;
+                pool_s0 = c * P.s_chunk;
+                const uint32_t s_n = P.s_count - pool_s0 < P.s_chunk ? P.s_count - pool_s0 : P.s_chunk;
                 pool_next = 0u;
-                pool_end = pool_valid * P.s_count;
+                pool_end = pool_valid * s_n;
             }
         }
         if (fresh) {

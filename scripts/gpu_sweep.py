@@ -13,10 +13,11 @@ import rtiow_rust_b200 as R  # noqa: E402
 CASES = {"book1": ("book1", 1200, 800, 50, True), "cornell": ("cornell", 800, 800, 100, False),
          "final": ("final", 800, 800, 100, False), "final_bvh": ("final", 800, 800, 100, True)}
 names = sys.argv[1:] or ["book1", "cornell", "final"]
-threads = [int(x) for x in os.environ.get("SWEEP_THREADS", "128,256,512").split(",")]
+threads = [int(x) for x in os.environ.get("SWEEP_THREADS", "0,512,768").split(",")]
 cps = [int(x) for x in os.environ.get("SWEEP_CPS", "0").split(",")]
 modes = [int(x) for x in os.environ.get("SWEEP_MODES", "0,1").split(",")]
 reps = int(os.environ.get("SWEEP_REPS", "3"))
+
 for key in names:
     name, nx, ny, ns, bvh = CASES[key]
     w, c = R.build_scene(name, nx, ny, use_bvh=bvh)

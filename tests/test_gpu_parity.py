@@ -93,10 +93,10 @@ def test_execution_shape_does_not_change_results():
     multi = R.par_cast(nx, ny, ns, cam, world).rgb
     assert world.stats()["passes"] > 1 and bits_equal(multi, ref)
     world.set_tuning(staging_mib=2048)
-    for threads in (128, 512):
+    for threads in (128, 256, 512, 1024):
         world.set_tuning(cta_threads=threads)
         assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, ref), threads
-    world.set_tuning(cta_threads=256, force_global=True)
+    world.set_tuning(cta_threads=0, force_global=True)
     assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, ref)
     assert world.stats()["scene_in_smem"] == 0
     world.set_tuning(ctas_per_sm=1)
