@@ -65,7 +65,7 @@ class Stats(C.Structure):
 # every symbol include/rtiow_b200.h declares
 ABI_SYMBOLS = ("rtiow_b200_abi_version", "rtiow_b200_last_error", "rtiow_b200_scene_validate",
                "rtiow_b200_scene_create", "rtiow_b200_scene_destroy", "rtiow_b200_release_cached_memory", "rtiow_b200_render", "rtiow_b200_render_rows",
-               "rtiow_b200_render_rows_device", "rtiow_b200_render_samples", "rtiow_b200_ppm_quantise",
+               "rtiow_b200_render_rows_device", "rtiow_b200_render_rows_strided_device", "rtiow_b200_render_samples", "rtiow_b200_ppm_quantise",
                "rtiow_b200_get_stats", "rtiow_b200_set_tuning", "rtiow_b200_set_traversal")
 
 _abi = None
@@ -95,6 +95,7 @@ def abi():
         L.rtiow_b200_render.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, vp]
         L.rtiow_b200_render_rows.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, u32, u32, vp]
         L.rtiow_b200_render_rows_device.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, u32, u32, vp, vp]
+        L.rtiow_b200_render_rows_strided_device.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, u32, u32, u32, vp, vp]
         L.rtiow_b200_render_samples.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, u32, u32, vp]
         L.rtiow_b200_ppm_quantise.argtypes = [vp, vp, C.c_size_t, vp]
         L.rtiow_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]

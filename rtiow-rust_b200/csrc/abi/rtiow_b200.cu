@@ -230,10 +230,11 @@ int ensure_uploaded(rtiow_scene* s, rtiow_scene::Blob& B) {
 }
 
 int check_render_args(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny, uint32_t ns, uint32_t r0,
-                      uint32_t r1, const void* out) {
+                      uint32_t r1, const void* out, uint32_t step = 1) {
     if (!s || !cam || !out) return set_err(RTIOW_ERR_INVALID_ARG, "null argument");
     if (nx == 0 || ny == 0 || ns == 0) return set_err(RTIOW_ERR_INVALID_ARG, "nx, ny and ns must be non-zero");
     if (r0 >= r1 || r1 > ny) return set_err(RTIOW_ERR_INVALID_ARG, "row range must satisfy row_begin < row_end <= ny");
+    if (step == 0) return set_err(RTIOW_ERR_INVALID_ARG, "row_step must be non-zero");
     if (static_cast<uint64_t>(nx) * ny >= (1ull << 32)) return set_err(RTIOW_ERR_INVALID_ARG, "image too large");
     if (!(cam->time0 < cam->time1))  // rand's gen_range asserts low < high (camera.rs:55)
         return set_err(RTIOW_ERR_INVALID_ARG, "Uniform::sample_single called with low >= high (camera exposure)");
@@ -242,9 +243,9 @@ int check_render_args(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, ui
 
 // Enqueue a full render of rows [r0, r1) into device buffer d_out (rgb floats) and/or d_samples.
 int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny, uint32_t ns, uint64_t seed,
-                   uint32_t r0, uint32_t r1, float* d_out, float4* d_samples, cudaStream_t stream) {
+                   uint32_t r0, uint32_t r1, float* d_out, float4* d_samples, cudaStream_t stream, uint32_t step = 1) {
     CK(cudaSetDevice(s->device));
-    const uint32_t n_rows = r1 - r0;
+    const uint32_t n_rows = (r1 - r0 + step - 1) / step;  // rows r0, r0 + step, ... below r1
     const uint64_t npix64 = static_cast<uint64_t>(n_rows) * nx;
     const uint32_t npix = static_cast<uint32_t>(npix64);
     const uint64_t budget = static_cast<uint64_t>(s->staging_mib) << 20;
@@ -280,7 +281,7 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     P.off_nodes = B.lay.off_nodes; P.off_frames = B.lay.off_frames; P.off_ops = B.lay.off_ops; P.off_mats = B.lay.off_mats;
     P.off_tex = B.lay.off_tex; P.off_pvecs = B.lay.off_pvecs; P.off_pperm = B.lay.off_pperm;
     std::memcpy(P.cam, cam, sizeof(float) * 21);
-    P.nx = nx; P.ny = ny; P.row_begin = r0; P.n_rows = n_rows;
+    P.nx = nx; P.ny = ny; P.row_begin = r0; P.n_rows = n_rows; P.row_step = step;
     P.npix = npix; P.n_groups = n_groups;
     P.key0 = static_cast<uint32_t>(seed); P.key1 = static_cast<uint32_t>(seed >> 32);
     P.bg_kind = s->bg_kind;
@@ -459,6 +460,13 @@ int rtiow_b200_render_rows_device(rtiow_scene_t* s, const rtiow_camera_t* cam, u
                                   uint64_t seed, uint32_t r0, uint32_t r1, float* d_out, void* cuda_stream) {
     if (int rc = check_render_args(s, cam, nx, ny, ns, r0, r1, d_out)) return rc;
     return enqueue_render(s, cam, nx, ny, ns, seed, r0, r1, d_out, nullptr, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int rtiow_b200_render_rows_strided_device(rtiow_scene_t* s, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny, uint32_t ns,
+                                          uint64_t seed, uint32_t r0, uint32_t r1, uint32_t step, float* d_out,
+                                          void* cuda_stream) {
+    if (int rc = check_render_args(s, cam, nx, ny, ns, r0, r1, d_out, step)) return rc;
+    return enqueue_render(s, cam, nx, ny, ns, seed, r0, r1, d_out, nullptr, static_cast<cudaStream_t>(cuda_stream), step);
 }
 
 int rtiow_b200_render_rows(rtiow_scene_t* s, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny, uint32_t ns, uint64_t seed,

@@ -30,7 +30,7 @@ struct KParams {
     uint32_t blob_bytes;
     uint32_t off_nodes, off_frames, off_ops, off_mats, off_tex, off_pvecs, off_pperm;
     float cam[21];              // rtiow_camera_t
-    uint32_t nx, ny, row_begin, n_rows;
+    uint32_t nx, ny, row_begin, n_rows, row_step;  // rows row_begin, row_begin + row_step, ... (n_rows of them)
     uint32_t s_begin, s_count;  // samples [s_begin, s_begin + s_count) of every pixel in this pass
     uint32_t npix, n_groups;
     uint32_t s_chunk, n_chunks, n_units;  // work unit = s_chunk samples of one 32-pixel group
@@ -297,7 +297,7 @@ RT_HD V3 in_unit_sphere(const Rng& rng, uint32_t bounce) {  // vec3.rs:19-26
 // ------------------------------------------------------------------------------------------------
 RT_HD void generate_camera_ray(const KParams& P, PathState& st) {
     const uint32_t r = st.pix / P.nx, x = st.pix - r * P.nx;
-    const uint32_t y = P.ny - 1u - (P.row_begin + r);  // (0..ny).rev()  lib.rs:326-330
+    const uint32_t y = P.ny - 1u - (P.row_begin + r * P.row_step);  // (0..ny).rev()  lib.rs:326-330
     st.rng.pixel = y * P.nx + x;
     st.rng.sample = st.samp;
     const U4 cw = st.rng.block(0u, PURPOSE_CAMERA, 0u);

@@ -1,9 +1,18 @@
-"""Multi-GPU sharding of par_cast: one process per GPU (torchrun), each rank renders a block of
-scanlines straight into its slice of the full framebuffer on its own device, then ONE in-place
-NCCL all-gather makes the frame whole on every rank (skipped when world_size == 1).
+"""Multi-GPU sharding of par_cast: one process per GPU (torchrun).  Scanlines are independent
+(src/lib.rs:324-332 parallelises exactly there) and the RNG is keyed by global pixel and sample index,
+so the assembled image is bit-identical for every world size.
 
-Scanlines are independent (src/lib.rs:324-332 parallelises exactly there) and the RNG is keyed by
-global pixel and sample index, so the gathered image is bit-identical for every world size.
+Two partitions of the rows:
+
+  interleaved (default)  rank r renders rows r, r + G, r + 2G, ...  Every GPU gets the same mix of cheap
+                         (sky: one segment) and expensive (ground, spheres) scanlines.  The ranks' packed
+                         row blocks are exchanged with ONE NCCL all-gather and de-interleaved by a single
+                         strided device copy.
+  contiguous             rank r renders rows [r*ny/G, (r+1)*ny/G) straight into its slice of the frame and
+                         the all-gather is in place (BASELINE.json's "scanline block" wording); simpler, but
+                         on the book-1 scene the top ranks finish early.
+
+No other collective exists on the path; with one rank nothing is exchanged at all.
 """
 import ctypes as C
 
@@ -14,60 +23,112 @@ from . import api
 
 
 class RowShard:
-    """Rows [begin, end) of rank `rank` out of `world_size`: contiguous blocks, the first
-    ny % world_size ranks get one extra row."""
+    """Which output rows (row 0 = top) rank `rank` of `world_size` renders."""
 
-    def __init__(self, ny, rank=0, world_size=1):
-        self.ny, self.rank, self.world_size = ny, rank, world_size
-        base, extra = divmod(ny, world_size)
-        self.counts = [base + (1 if r < extra else 0) for r in range(world_size)]
-        self.begins = [sum(self.counts[:r]) for r in range(world_size)]
-        self.begin = self.begins[rank]
-        self.end = self.begin + self.counts[rank]
-        self.uniform = extra == 0
+    def __init__(self, ny, rank=0, world_size=1, interleaved=True):
+        self.ny, self.rank, self.world_size, self.interleaved = ny, rank, world_size, bool(interleaved)
+        if self.interleaved:
+            self.counts = [(ny - r + world_size - 1) // world_size if r < ny else 0 for r in range(world_size)]
+            self.begin, self.end, self.step = min(rank, ny), ny, world_size
+        else:
+            base, extra = divmod(ny, world_size)
+            self.counts = [base + (1 if r < extra else 0) for r in range(world_size)]
+            self.begins = [sum(self.counts[:r]) for r in range(world_size)]
+            self.begin = self.begins[rank]
+            self.end = self.begin + self.counts[rank]
+            self.step = 1
+        self.n_rows = self.counts[rank]
+        self.max_rows = max(self.counts)
+        self.uniform = len(set(self.counts)) == 1
+
+    def rows(self, rank=None):
+        """Global row indices of a rank, in the order they are packed."""
+        r = self.rank if rank is None else rank
+        if self.interleaved:
+            return list(range(r, self.ny, self.world_size))
+        b = sum(self.counts[:r])
+        return list(range(b, b + self.counts[r]))
 
     def describe(self):
-        return f"{self.counts[0]} rows x {self.world_size} rank(s), contiguous blocks"
+        kind = "interleaved rows (rank r: r, r+G, ...)" if self.interleaved else "contiguous blocks"
+        return f"{self.max_rows} rows x {self.world_size} rank(s), {kind}"
 
 
-def render_sharded_device(nx, ny, ns, camera, world, frame, shard, seed=api.DEFAULT_SEED):
-    """Device-resident step: render this rank's rows into `frame` ([ny, nx, 3] CUDA float32), then
-    all-gather.  Everything is enqueued on the current stream; nothing is synchronised."""
+def assemble(parts, shard, xp=np):
+    """[world_size, max_rows, nx, 3] packed blocks -> [ny, nx, 3] frame.  Works on numpy arrays and
+    torch tensors (one strided copy)."""
+    G, mx = shard.world_size, shard.max_rows
+    if shard.interleaved:
+        # row lr of rank r is global row lr * G + r
+        nx = parts.shape[2]
+        if xp is np:
+            return np.ascontiguousarray(parts.transpose(1, 0, 2, 3).reshape(mx * G, nx, 3)[:shard.ny])
+        return parts.permute(1, 0, 2, 3).reshape(mx * G, nx, 3)[:shard.ny].contiguous()
+    pieces = [parts[r, :c] for r, c in enumerate(shard.counts)]
+    if xp is np:
+        return np.concatenate(pieces)
     import torch
+    return torch.cat(pieces)
+
+
+class ShardBuffers:
+    """Device buffers of one rank, allocated once: `mine` (this rank's packed rows, padded to max_rows),
+    `parts` (everybody's), `frame` (the assembled image)."""
+
+    def __init__(self, nx, ny, shard, device):
+        import torch
+        self.shard = shard
+        self.frame = torch.empty((ny, nx, 3), dtype=torch.float32, device=device)
+        if shard.world_size == 1:
+            self.mine = self.frame
+            self.parts = None
+        elif shard.interleaved or not shard.uniform:
+            self.parts = torch.zeros((shard.world_size, shard.max_rows, nx, 3), dtype=torch.float32, device=device)
+            self.mine = self.parts[shard.rank]          # gather in place: send = recv + rank * count
+        else:
+            self.parts = None
+            self.mine = self.frame[shard.begin:shard.end]
+
+
+def render_sharded_device(nx, ny, ns, camera, world, bufs, seed=api.DEFAULT_SEED):
+    """Device-resident step: render this rank's rows, all-gather, assemble into bufs.frame.  Everything is
+    enqueued on the current stream; nothing is synchronised."""
     import torch.distributed as dist
-    if shard.end > shard.begin:
-        api.render_rows_device(nx, ny, ns, camera, world, frame[shard.begin:shard.end], (shard.begin, shard.end), seed=seed)
-    if shard.world_size > 1:
-        if shard.uniform:
-            dist.all_gather_into_tensor(frame, frame[shard.begin:shard.end])  # in place: send = recv + rank*count
-        else:  # ragged split: gather equal-sized padded blocks, then place each rank's rows
-            mx = max(shard.counts)
-            mine = torch.zeros((mx, nx, 3), dtype=frame.dtype, device=frame.device)
-            mine[:shard.end - shard.begin] = frame[shard.begin:shard.end]
-            allb = torch.empty((shard.world_size, mx, nx, 3), dtype=frame.dtype, device=frame.device)
-            dist.all_gather_into_tensor(allb, mine)
-            for r, (b, c) in enumerate(zip(shard.begins, shard.counts)):
-                frame[b:b + c] = allb[r, :c]
-    return frame
+    sh = bufs.shard
+    if sh.n_rows > 0:
+        api.render_rows_device(nx, ny, ns, camera, world, bufs.mine, (sh.begin, sh.end), seed=seed, row_step=sh.step)
+    if sh.world_size > 1:
+        if bufs.parts is not None:
+            dist.all_gather_into_tensor(bufs.parts.view(sh.world_size * sh.max_rows, nx, 3), bufs.mine)
+            bufs.frame.copy_(assemble(bufs.parts, sh, xp=None))
+        else:
+            dist.all_gather_into_tensor(bufs.frame, bufs.mine)   # contiguous, equal blocks: in place
+    return bufs.frame
 
 
-def par_cast_e2e(nx, ny, ns, camera, world, frame, pinned_out, shard, seed=api.DEFAULT_SEED):
-    """End-to-end step with host buffers: scene descriptor H2D (fresh upload), render, gather, frame D2H
-    into pinned host memory on rank 0.  Returns (h2d_bytes, d2h_bytes) of this rank."""
+def par_cast_e2e(nx, ny, ns, camera, world, bufs, host_out, seed=api.DEFAULT_SEED):
+    """End-to-end step with host buffers.  One rank: exactly the C ABI's host call — scene descriptor
+    H2D (fresh rtiow_b200_scene_create), rtiow_b200_render into `host_out` (numpy, pageable).  Several ranks:
+    fresh scene upload, sharded render, all-gather, frame D2H into `host_out` (pinned torch tensor) on rank 0.
+    Returns (h2d_bytes, d2h_bytes) of this rank."""
     import torch
-    dev = frame.device.index or 0
+    sh = bufs.shard
+    dev = bufs.frame.device.index or 0
     world.upload_fresh(dev)
-    render_sharded_device(nx, ny, ns, camera, world, frame, shard, seed=seed)
     h2d = world.stats(dev)["scene_bytes"] + C.sizeof(N.CameraRec)
+    if sh.world_size == 1:
+        api._check(N.abi().rtiow_b200_render(world.gpu(dev), C.byref(camera.rec), nx, ny, ns, seed, host_out.ctypes.data))
+        return h2d, host_out.nbytes
+    render_sharded_device(nx, ny, ns, camera, world, bufs, seed=seed)
     d2h = 0
-    if shard.rank == 0:
-        pinned_out.copy_(frame, non_blocking=True)
-        d2h = frame.numel() * 4
+    if sh.rank == 0:
+        host_out.copy_(bufs.frame, non_blocking=True)
+        d2h = bufs.frame.numel() * 4
     torch.cuda.current_stream(dev).synchronize()
     return h2d, d2h
 
 
-def par_cast_distributed(nx, ny, ns, camera, world, seed=api.DEFAULT_SEED):
+def par_cast_distributed(nx, ny, ns, camera, world, seed=api.DEFAULT_SEED, interleaved=True):
     """par_cast across the ranks of the default process group (NCCL on GPUs).  Every rank returns the
     whole Image."""
     import torch
@@ -75,19 +136,18 @@ def par_cast_distributed(nx, ny, ns, camera, world, seed=api.DEFAULT_SEED):
     rank = dist.get_rank() if dist.is_initialized() else 0
     ws = dist.get_world_size() if dist.is_initialized() else 1
     dev = torch.cuda.current_device()
-    frame = torch.empty((ny, nx, 3), dtype=torch.float32, device=f"cuda:{dev}")
-    render_sharded_device(nx, ny, ns, camera, world, frame, RowShard(ny, rank, ws), seed=seed)
-    return api.Image(frame.cpu().numpy())
+    bufs = ShardBuffers(nx, ny, RowShard(ny, rank, ws, interleaved), f"cuda:{dev}")
+    render_sharded_device(nx, ny, ns, camera, world, bufs, seed=seed)
+    return api.Image(bufs.frame.cpu().numpy())
 
 
 def gather_rows_cpu(local_rows, shard, nx):
-    """The same assembly over any backend (used by the gloo tests on CPU): concatenates the ranks'
-    row blocks in rank order.  `local_rows` is a [rows, nx, 3] float32 numpy array."""
+    """The same exchange + assembly over any backend (used by the gloo tests on CPU).  `local_rows` is this
+    rank's packed [n_rows, nx, 3] float32 numpy array."""
     import torch
     import torch.distributed as dist
-    mx = max(shard.counts)
-    mine = torch.zeros((mx, nx, 3), dtype=torch.float32)
+    mine = torch.zeros((shard.max_rows, nx, 3), dtype=torch.float32)
     mine[:local_rows.shape[0]] = torch.from_numpy(np.ascontiguousarray(local_rows, np.float32))
-    parts = [torch.empty((mx, nx, 3), dtype=torch.float32) for _ in shard.counts]
-    dist.all_gather(parts, mine)
-    return torch.cat([p[:c] for p, c in zip(parts, shard.counts)]).numpy()
+    parts = torch.empty((shard.world_size, shard.max_rows, nx, 3), dtype=torch.float32)
+    dist.all_gather_into_tensor(parts.view(shard.world_size * shard.max_rows, nx, 3), mine)
+    return assemble(parts.numpy(), shard)

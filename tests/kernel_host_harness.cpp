@@ -15,7 +15,7 @@
 // accel != 0: the re-indexed (SAH, ordered) traversal the device uses; 0: the plain reference-order stream.
 extern "C" int harness_render(const rtiow_scene_desc_t* desc, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny,
                               uint32_t ns, uint64_t seed, uint32_t row_begin, uint32_t row_end, float* out_rgb,
-                              float* out_samples, int accel, uint32_t* layout_out) {
+                              float* out_samples, int accel, uint32_t* layout_out, uint32_t row_step) {
     using namespace rtiow;
     bool has_frames = false, uses_perlin = false;
     std::string msg;
@@ -29,7 +29,9 @@ extern "C" int harness_render(const rtiow_scene_desc_t* desc, const rtiow_camera
     P.off_nodes = lay.off_nodes; P.off_frames = lay.off_frames; P.off_ops = lay.off_ops; P.off_mats = lay.off_mats; P.off_tex = lay.off_tex;
     P.off_pvecs = lay.off_pvecs; P.off_pperm = lay.off_pperm;
     std::memcpy(P.cam, cam, sizeof(float) * 21);
-    P.nx = nx; P.ny = ny; P.row_begin = row_begin; P.n_rows = row_end - row_begin;
+    if (row_step == 0) row_step = 1;
+    P.nx = nx; P.ny = ny; P.row_begin = row_begin; P.row_step = row_step;
+    P.n_rows = (row_end - row_begin + row_step - 1) / row_step;  // rows row_begin, +step, ... below row_end
     P.s_begin = 0; P.s_count = ns;
     P.npix = P.n_rows * nx;
     P.key0 = static_cast<uint32_t>(seed); P.key1 = static_cast<uint32_t>(seed >> 32);

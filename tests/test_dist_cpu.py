@@ -24,7 +24,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world_size, port, ny, out_dir):
+def _worker(rank, world_size, port, ny, interleaved, out_dir):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -34,21 +34,23 @@ def _worker(rank, world_size, port, ny, out_dir):
     from rtiow_rust_b200 import dist as rdist
     nx, ns = 40, 3
     world, cam = R.build_scene("kitchen_sink", nx, ny, use_bvh=True)
-    shard = rdist.RowShard(ny, rank, world_size)
-    local, _ = H.render(world, cam, nx, ny, ns, rows=(shard.begin, shard.end))
+    shard = rdist.RowShard(ny, rank, world_size, interleaved)
+    local, _ = H.render(world, cam, nx, ny, ns, rows=(shard.begin, shard.end), row_step=shard.step)
+    assert local.shape[0] == shard.n_rows
     full = rdist.gather_rows_cpu(local, shard, nx)
     np.save(os.path.join(out_dir, f"rank{rank}.npy"), full)
     dist.barrier()
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("interleaved", [True, False])
 @pytest.mark.parametrize("ny", [30, 31])   # 31: uneven split (16 + 15 rows)
-def test_two_rank_row_sharding_is_bit_identical(tmp_path, ny):
+def test_two_rank_row_sharding_is_bit_identical(tmp_path, ny, interleaved):
     sys.path.insert(0, HERE)
     import harness_lib as H
     import rtiow_rust_b200 as R
     H.lib()  # build once, before forking
-    mp.spawn(_worker, args=(2, _free_port(), ny, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), ny, interleaved, str(tmp_path)), nprocs=2, join=True)
     world, cam = R.build_scene("kitchen_sink", 40, ny, use_bvh=True)
     want, _ = H.render(world, cam, 40, ny, 3)
     for r in range(2):
@@ -57,9 +59,21 @@ def test_two_rank_row_sharding_is_bit_identical(tmp_path, ny):
 
 
 def test_row_shard_partition():
-    from rtiow_rust_b200.dist import RowShard
-    for ny, ws in ((800, 8), (800, 3), (5, 8), (1, 2)):
-        shards = [RowShard(ny, r, ws) for r in range(ws)]
-        assert shards[0].begin == 0 and shards[-1].end == ny
-        assert all(a.end == b.begin for a, b in zip(shards, shards[1:]))
-        assert max(s.end - s.begin for s in shards) - min(s.end - s.begin for s in shards) <= 1
+    from rtiow_rust_b200.dist import RowShard, assemble
+    for ny, ws in ((800, 8), (800, 3), (5, 8), (1, 2), (3200, 8)):
+        for inter in (True, False):
+            shards = [RowShard(ny, r, ws, inter) for r in range(ws)]
+            rows = sorted(sum((s.rows() for s in shards), []))
+            assert rows == list(range(ny)), (ny, ws, inter)                       # every row exactly once
+            assert all(len(s.rows()) == s.n_rows for s in shards)
+            assert max(s.n_rows for s in shards) - min(s.n_rows for s in shards) <= 1
+            # assemble() puts packed row lr of rank r back at its global row
+            parts = np.full((ws, shards[0].max_rows, 2, 3), -1, np.float32)
+            for s in shards:
+                for lr, g in enumerate(s.rows()):
+                    parts[s.rank, lr] = g
+            frame = assemble(parts, shards[0])
+            assert frame.shape == (ny, 2, 3) and np.array_equal(frame[:, 0, 0], np.arange(ny, dtype=np.float32))
+    # interleaving balances the book-1 frame: each rank's rows span the whole image
+    s = RowShard(800, 3, 8)
+    assert s.rows()[0] == 3 and s.rows()[-1] == 795 and s.step == 8

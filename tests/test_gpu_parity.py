@@ -82,6 +82,27 @@ def test_row_blocks_are_bit_identical_to_the_full_image():
         assert bits_equal(part, full[r0:r1]), (r0, r1)
 
 
+def test_strided_rows_and_workspace_reuse():
+    """The multi-GPU unit `rows r, r + G, ...` equals the same rows of the whole image, and scenes created
+    after another one was destroyed (they inherit its cached device buffers) render the same bits."""
+    import torch
+    nx, ny, ns = 70, 45, 5
+    world, cam = R.build_scene("kitchen_sink", nx, ny, use_bvh=True)
+    full = R.par_cast(nx, ny, ns, cam, world).rgb
+    for begin, step in ((0, 2), (1, 2), (3, 8), (44, 8), (0, 1)):
+        n = (ny - begin + step - 1) // step
+        out = torch.empty((n, nx, 3), dtype=torch.float32, device="cuda:0")
+        api.render_rows_device(nx, ny, ns, cam, world, out, (begin, ny), row_step=step)
+        torch.cuda.synchronize()
+        assert bits_equal(out.cpu().numpy(), full[begin::step]), (begin, step)
+    for _ in range(3):
+        world.upload_fresh(0)
+        assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, full)
+    N.abi().rtiow_b200_release_cached_memory()
+    world.upload_fresh(0)
+    assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, full)
+
+
 def test_execution_shape_does_not_change_results():
     """Sample passes, CTA size, residency (shared vs global memory) and occupancy are scheduling
     only: the image must not move by one bit."""
