@@ -30,6 +30,13 @@ extern "C" {
 
 #define RTIOW_B200_ABI_VERSION 1u
 
+/* The shared library exports these entry points and nothing else. */
+#if defined(__GNUC__)
+#define RTIOW_API __attribute__((visibility("default")))
+#else
+#define RTIOW_API
+#endif
+
 enum {
     RTIOW_OK = 0,
     RTIOW_ERR_INVALID_ARG = 1,  /* null pointer, zero size, low >= high exposure ...             */
@@ -171,70 +178,74 @@ typedef struct rtiow_stats_t {
     uint32_t grid, block, dyn_smem_bytes, regs_per_thread;
     uint32_t accel_nodes;    /* nodes of the library's own index over the scene's Bvh subtrees (0 = none) */
     uint32_t accel_subtrees; /* how many Bvh subtrees were re-indexed                                      */
+    uint32_t traversal;      /* RTIOW_TRAVERSAL_*: how the last render walked Bvh subtrees                 */
 } rtiow_stats_t;
 
 typedef struct rtiow_scene rtiow_scene_t;
 
-int rtiow_b200_abi_version(void);
-const char* rtiow_b200_last_error(void);
+RTIOW_API int rtiow_b200_abi_version(void);
+RTIOW_API const char* rtiow_b200_last_error(void);
 
 /* Checks `desc` exactly as rtiow_b200_scene_create does, without touching a GPU. */
-int rtiow_b200_scene_validate(const rtiow_scene_desc_t* desc);
+RTIOW_API int rtiow_b200_scene_validate(const rtiow_scene_desc_t* desc);
 
 /* Validates `desc`, copies it to `device` (CUDA ordinal) and returns a handle. */
-int rtiow_b200_scene_create(const rtiow_scene_desc_t* desc, int device, rtiow_scene_t** out);
-void rtiow_b200_scene_destroy(rtiow_scene_t* scene);
+RTIOW_API int rtiow_b200_scene_create(const rtiow_scene_desc_t* desc, int device, rtiow_scene_t** out);
+RTIOW_API void rtiow_b200_scene_destroy(rtiow_scene_t* scene);
 /* Destroyed scenes leave their device work buffers in a small per-device cache for the next
  * scene_create; this frees them. */
-void rtiow_b200_release_cached_memory(void);
+RTIOW_API void rtiow_b200_release_cached_memory(void);
 
 /* par_cast (src/lib.rs:363-376) with an explicit seed: out_rgb receives ny*nx*3 floats, row 0 =
  * TOP scanline (lib.rs:326-330), linear (pre-gamma), already divided by ns (lib.rs:374) — i.e.
  * exactly `Image`.  Samples of a pixel are summed left to right from 0 in sample order
  * (src/vec3.rs:195-203).  out_rgb is HOST memory. */
-int rtiow_b200_render(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny, uint32_t ns,
+RTIOW_API int rtiow_b200_render(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny, uint32_t ns,
                       uint64_t seed, float* out_rgb);
 
 /* Rows [row_begin, row_end) of the same image (row 0 = top): the unit of multi-GPU sharding.
  * The result is bit-identical to the corresponding rows of rtiow_b200_render. */
-int rtiow_b200_render_rows(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny, uint32_t ns,
+RTIOW_API int rtiow_b200_render_rows(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny, uint32_t ns,
                            uint64_t seed, uint32_t row_begin, uint32_t row_end, float* out_rows);
 
 /* Same, but `d_out_rows` is DEVICE memory on the scene's device and the work is only enqueued on
  * `cuda_stream` (a cudaStream_t, NULL = default stream); nothing is synchronised. */
-int rtiow_b200_render_rows_device(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny,
+RTIOW_API int rtiow_b200_render_rows_device(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny,
                                   uint32_t ns, uint64_t seed, uint32_t row_begin, uint32_t row_end,
                                   float* d_out_rows, void* cuda_stream);
 
 /* Rows row_begin, row_begin + row_step, ... below row_end, packed in that order: with
  * row_begin = rank and row_step = n_ranks every GPU gets an equal mix of cheap (sky) and expensive
  * scanlines.  Each row is bit-identical to the same row of rtiow_b200_render. */
-int rtiow_b200_render_rows_strided_device(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny,
+RTIOW_API int rtiow_b200_render_rows_strided_device(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny,
                                           uint32_t ns, uint64_t seed, uint32_t row_begin, uint32_t row_end,
                                           uint32_t row_step, float* d_out_rows, void* cuda_stream);
 
 /* Parity/debug: per-sample radiance before the fold, HOST memory,
  * (row_end-row_begin)*nx*ns*4 floats laid out [row][x][sample]{r,g,b,segments}. */
-int rtiow_b200_render_samples(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny,
+RTIOW_API int rtiow_b200_render_samples(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny,
                               uint32_t ns, uint64_t seed, uint32_t row_begin, uint32_t row_end, float* out_samples);
 
 /* print_ppm's per-channel sqrt + to_u8 (src/lib.rs:344-361) on the device: n floats -> n bytes. */
-int rtiow_b200_ppm_quantise(rtiow_scene_t* scene, const float* linear, size_t n, uint8_t* out);
+RTIOW_API int rtiow_b200_ppm_quantise(rtiow_scene_t* scene, const float* linear, size_t n, uint8_t* out);
 
 /* Synchronises the scene's device and reports the last render. */
-int rtiow_b200_get_stats(rtiow_scene_t* scene, rtiow_stats_t* out);
+RTIOW_API int rtiow_b200_get_stats(rtiow_scene_t* scene, rtiow_stats_t* out);
 
 /* Tuning knobs (0 = default / automatic): threads per CTA (128..1024), CTAs per SM, staging budget in MiB,
  * force_global != 0 keeps the scene in global memory even if it fits shared memory. */
-int rtiow_b200_set_tuning(rtiow_scene_t* scene, uint32_t cta_threads, uint32_t ctas_per_sm, uint32_t staging_mib,
+RTIOW_API int rtiow_b200_set_tuning(rtiow_scene_t* scene, uint32_t cta_threads, uint32_t ctas_per_sm, uint32_t staging_mib,
                           int force_global);
 
-/* How `Bvh` subtrees (src/bvh.rs) are walked.  Both give the same image bit for bit; the choice is
- * speed only.  REINDEXED (default): the library indexes the subtree's leaves with its own tree and
- * visits the nearer child first.  REFERENCE_ORDER: the boxes exactly as flattened, left first, like
- * Bvh::hit (src/bvh.rs:85-120). */
-enum { RTIOW_TRAVERSAL_REINDEXED = 0, RTIOW_TRAVERSAL_REFERENCE_ORDER = 1 };
-int rtiow_b200_set_traversal(rtiow_scene_t* scene, int mode);
+/* How `Bvh` subtrees (src/bvh.rs) are walked.  All give the same image bit for bit; the choice is
+ * speed only.  REINDEXED (default): the library indexes the subtree's leaves with its own tree,
+ * visits the nearer child first, culls inner boxes with a cheaper test that never rejects what the
+ * reference's Aabb::hit accepts, and runs the reference's Aabb::hit on each leaf's own box before
+ * its primitives.  REINDEXED_EXACT: the same tree with the reference's Aabb::hit arithmetic at
+ * every node (smaller device image; picked automatically when only that fits in shared memory).
+ * REFERENCE_ORDER: the boxes exactly as flattened, left first, like Bvh::hit (src/bvh.rs:85-120). */
+enum { RTIOW_TRAVERSAL_REINDEXED = 0, RTIOW_TRAVERSAL_REFERENCE_ORDER = 1, RTIOW_TRAVERSAL_REINDEXED_EXACT = 2 };
+RTIOW_API int rtiow_b200_set_traversal(rtiow_scene_t* scene, int mode);
 
 #ifdef __cplusplus
 }

@@ -138,8 +138,13 @@ class World:
         _check(N.abi().rtiow_b200_set_tuning(self.gpu(device), cta_threads, ctas_per_sm, staging_mib, int(force_global)))
 
     def set_traversal(self, mode, device=0):
-        """0 = re-indexed Bvh subtrees (default), 1 = the reference's own visiting order.  Same image either way."""
+        """0 = re-indexed Bvh subtrees, conservative inner box test (default); 1 = the reference's own visiting
+        order; 2 = re-indexed with the reference's box test at every node.  Same image every way."""
         _check(N.abi().rtiow_b200_set_traversal(self.gpu(device), int(mode)))
+
+    def scene_bytes(self, device=0):
+        """Bytes of the device image of the scene the last render used (uploaded by scene_create)."""
+        return self.stats(device)["scene_bytes"]
 
     def stats(self, device=0):
         st = N.Stats()

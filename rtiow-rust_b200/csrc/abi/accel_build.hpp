@@ -35,6 +35,37 @@ struct AccelNode {  // 64 bytes = 4 x float4
 };
 static_assert(sizeof(AccelNode) == 64, "AccelNode must be 64 bytes");
 
+// The same node for the conservative test (path_logic.cuh trav_node_step_fast): per axis the four
+// planes {child0 min, child0 max, child1 min, child1 max} and the same quad with min/max swapped, so
+// that a ray reads its near/far-ordered planes with one 16-byte load per axis (which of the two
+// quads depends only on the sign of its direction); then the links and `m`, the largest
+// |coordinate| in the node (+inf when it is too large for the error bound to be trusted).
+struct FastNode {  // 112 bytes = 7 x float4
+    float ax[3][2][4];
+    uint32_t link0, link1;
+    float m;
+    uint32_t pad;
+};
+static_assert(sizeof(FastNode) == 112, "FastNode must be 112 bytes");
+
+inline FastNode to_fast_node(const AccelNode& n) {
+    FastNode f{};
+    const bool has1 = n.link1 != kLinkEmpty;
+    float m = 1e-30f;  // never 0: the "test nothing" slack is m * inf
+    for (int a = 0; a < 3; ++a) {
+        const float q[4] = {n.c0_min[a], n.c0_max[a], n.c1_min[a], n.c1_max[a]};
+        const float w[4] = {n.c0_max[a], n.c0_min[a], n.c1_max[a], n.c1_min[a]};
+        std::memcpy(f.ax[a][0], q, 16);
+        std::memcpy(f.ax[a][1], w, 16);
+        for (int k = 0; k < (has1 ? 4 : 2); ++k) m = std::fmax(m, std::fabs(q[k]));
+    }
+    if (!(m <= 67108864.f)) m = std::numeric_limits<float>::infinity();  // 2^26; also catches NaN
+    f.link0 = n.link0;
+    f.link1 = n.link1;
+    f.m = m;
+    return f;
+}
+
 namespace accel_detail {
 
 struct Box {
@@ -43,7 +74,8 @@ struct Box {
         for (int a = 0; a < 3; ++a) { mn[a] = std::numeric_limits<float>::infinity(); mx[a] = -std::numeric_limits<float>::infinity(); }
     }
     void grow(const float* omn, const float* omx) {  // exact min/max: the union is representable
-        for (int a = 0; a < 3; ++a) { mn[a] = std::fmin(mn[a], omn[a]); mx[a] = std::fmax(mx[a], omx[a]); }
+        // a NaN coordinate is ignored, like fmin/fmax (which do not inline)
+        for (int a = 0; a < 3; ++a) { mn[a] = omn[a] < mn[a] ? omn[a] : mn[a]; mx[a] = omx[a] > mx[a] ? omx[a] : mx[a]; }
     }
     double half_area() const {
         const double dx = static_cast<double>(mx[0]) - mn[0], dy = static_cast<double>(mx[1]) - mn[1], dz = static_cast<double>(mx[2]) - mn[2];
@@ -58,54 +90,72 @@ inline int ceil_log2(size_t n) {
     return k;
 }
 
+// Full-sweep SAH over per-axis presorted leaf lists: every range [b, e) of idx[0], idx[1], idx[2]
+// holds the same leaves, each sorted by centroid on its axis (ties by leaf number), so a node costs
+// three linear sweeps and three stable partitions — O(n log n) for the whole tree.
 struct Builder {
     const std::vector<AccelLeaf>& leaves;
     std::vector<AccelNode>& nodes;
-    std::vector<uint32_t> order;  // permutation of leaf indices, partitioned in place
+    std::vector<uint32_t> idx[3];
+    std::vector<unsigned char> left_side;
+    std::vector<uint32_t> scratch;
+    std::vector<double> right_area;
     int max_depth_seen = 0;
+
+    Builder(const std::vector<AccelLeaf>& l, std::vector<AccelNode>& n) : leaves(l), nodes(n) {
+        const size_t count = leaves.size();
+        for (int axis = 0; axis < 3; ++axis) {
+            idx[axis].resize(count);
+            for (size_t i = 0; i < count; ++i) idx[axis][i] = static_cast<uint32_t>(i);
+            std::stable_sort(idx[axis].begin(), idx[axis].end(), [&](uint32_t a, uint32_t b) {
+                return leaves[a].mn[axis] + leaves[a].mx[axis] < leaves[b].mn[axis] + leaves[b].mx[axis];
+            });
+        }
+        left_side.assign(count, 0);
+        scratch.resize(count);
+        right_area.resize(count + 1);
+    }
 
     static uint32_t leaf_link(const AccelLeaf& l) { return kLinkLeaf | (l.count << 24) | l.first; }
 
-    Box bounds(size_t b, size_t e) const {
-        Box bx; bx.reset();
-        for (size_t i = b; i < e; ++i) bx.grow(leaves[order[i]].mn, leaves[order[i]].mx);
-        return bx;
+    // Moves the leaves flagged in left_side to the front of every axis list, keeping their order.
+    void partition(size_t b, size_t e) {
+        for (int axis = 0; axis < 3; ++axis) {
+            std::vector<uint32_t>& v = idx[axis];
+            size_t nl = b, nr = 0;
+            for (size_t i = b; i < e; ++i) {
+                if (left_side[v[i]]) v[nl++] = v[i];
+                else scratch[nr++] = v[i];
+            }
+            std::copy(scratch.begin(), scratch.begin() + static_cast<std::ptrdiff_t>(nr), v.begin() + static_cast<std::ptrdiff_t>(nl));
+        }
     }
 
-    // Returns the link of the subtree over order[b, e) and its box.
+    // Returns the link of the subtree over the leaves in [b, e) and its box.
     uint32_t build(size_t b, size_t e, int depth, Box* out_box) {
         max_depth_seen = std::max(max_depth_seen, depth);
         const size_t n = e - b;
         if (n == 1) {
-            const AccelLeaf& l = leaves[order[b]];
+            const AccelLeaf& l = leaves[idx[0][b]];
             std::memcpy(out_box->mn, l.mn, 12);
             std::memcpy(out_box->mx, l.mx, 12);
             return leaf_link(l);
         }
-        size_t split = b + n / 2;
         int split_axis = -1;
+        size_t best_i = n / 2;
         const bool force_median = (kAccelMaxDepth - depth) <= ceil_log2(n) + 1;
         if (!force_median) {
             double best_cost = std::numeric_limits<double>::max();
-            size_t best_i = 0;
-            std::vector<uint32_t> tmp(order.begin() + static_cast<std::ptrdiff_t>(b), order.begin() + static_cast<std::ptrdiff_t>(e));
-            std::vector<double> right_area(n);
-            auto sort_axis = [&](int axis) {
-                std::copy(order.begin() + static_cast<std::ptrdiff_t>(b), order.begin() + static_cast<std::ptrdiff_t>(e), tmp.begin());
-                std::stable_sort(tmp.begin(), tmp.end(), [&](uint32_t l, uint32_t r) {
-                    return leaves[l].mn[axis] + leaves[l].mx[axis] < leaves[r].mn[axis] + leaves[r].mx[axis];
-                });
-            };
             for (int axis = 0; axis < 3; ++axis) {
-                sort_axis(axis);
+                const uint32_t* v = idx[axis].data() + b;
                 Box acc; acc.reset();
                 for (size_t i = n; i-- > 1;) {
-                    acc.grow(leaves[tmp[i]].mn, leaves[tmp[i]].mx);
+                    acc.grow(leaves[v[i]].mn, leaves[v[i]].mx);
                     right_area[i] = acc.half_area();
                 }
                 acc.reset();
                 for (size_t i = 1; i < n; ++i) {
-                    acc.grow(leaves[tmp[i - 1]].mn, leaves[tmp[i - 1]].mx);
+                    acc.grow(leaves[v[i - 1]].mn, leaves[v[i - 1]].mx);
                     const double cost = acc.half_area() * static_cast<double>(i) + right_area[i] * static_cast<double>(n - i);
                     if (cost < best_cost) {
                         best_cost = cost;
@@ -114,25 +164,22 @@ struct Builder {
                     }
                 }
             }
-            if (split_axis >= 0) {
-                sort_axis(split_axis);
-                std::copy(tmp.begin(), tmp.end(), order.begin() + static_cast<std::ptrdiff_t>(b));
-                split = b + best_i;
-            }
         }
         if (split_axis < 0) {  // median on the widest axis (also the NaN / depth-limit fallback)
-            const Box bx = bounds(b, e);
-            int axis = 0;
+            Box bx; bx.reset();
+            for (size_t i = b; i < e; ++i) bx.grow(leaves[idx[0][i]].mn, leaves[idx[0][i]].mx);
             float ext = -1.f;
+            split_axis = 0;
             for (int a = 0; a < 3; ++a) {
                 const float x = bx.mx[a] - bx.mn[a];
-                if (x > ext) { ext = x; axis = a; }
+                if (x > ext) { ext = x; split_axis = a; }
             }
-            std::stable_sort(order.begin() + static_cast<std::ptrdiff_t>(b), order.begin() + static_cast<std::ptrdiff_t>(e), [&](uint32_t l, uint32_t r) {
-                return leaves[l].mn[axis] + leaves[l].mx[axis] < leaves[r].mn[axis] + leaves[r].mx[axis];
-            });
-            split = b + n / 2;
+            best_i = n / 2;
         }
+        const uint32_t* v = idx[split_axis].data() + b;
+        for (size_t i = 0; i < n; ++i) left_side[v[i]] = i < best_i ? 1 : 0;
+        partition(b, e);
+        const size_t split = b + best_i;
         const uint32_t me = static_cast<uint32_t>(nodes.size());
         nodes.push_back(AccelNode{});
         Box b0, b1;
@@ -155,9 +202,6 @@ struct Builder {
 // and returns the index of the root node.  A single leaf gets a root node with one empty slot so
 // that its box test still happens.
 inline uint32_t accel_build(const std::vector<AccelLeaf>& leaves, std::vector<AccelNode>* nodes, int* depth_out) {
-    accel_detail::Builder bd{leaves, *nodes, {}, 0};
-    bd.order.resize(leaves.size());
-    for (size_t i = 0; i < leaves.size(); ++i) bd.order[i] = static_cast<uint32_t>(i);
     if (leaves.size() == 1) {
         AccelNode nd{};
         std::memcpy(nd.c0_min, leaves[0].mn, 12); std::memcpy(nd.c0_max, leaves[0].mx, 12);
@@ -168,6 +212,7 @@ inline uint32_t accel_build(const std::vector<AccelLeaf>& leaves, std::vector<Ac
         if (depth_out) *depth_out = 1;
         return static_cast<uint32_t>(nodes->size() - 1);
     }
+    accel_detail::Builder bd(leaves, *nodes);
     accel_detail::Box root_box;
     const uint32_t root = bd.build(0, leaves.size(), 0, &root_box);
     if (depth_out) *depth_out = bd.max_depth_seen;

@@ -1,0 +1,21 @@
+// The megakernel instantiations live in their own translation units (csrc/kernels/*.cu) so that
+// they compile in parallel; the ABI implementation picks one through these functions.
+#pragma once
+#include <cstdint>
+
+#include "../device/path_logic.cuh"
+
+namespace rtiow {
+
+typedef void (*kernel_fn)(const KParams);
+
+struct KernelVariant {
+    kernel_fn fn;   // nullptr: no such instantiation
+    int threads;
+};
+
+// render_kernel (render_kernel.cuh): one path per lane.  threads in {256, 512, 768}.
+KernelVariant pick_plain_smem(bool frames, bool fast, uint32_t threads);
+KernelVariant pick_plain_global(bool frames, bool fast, uint32_t threads);
+
+}  // namespace rtiow

@@ -11,7 +11,8 @@
 #include <vector>
 
 #include "../../../include/rtiow_b200.h"
-#include "../device/render_kernel.cuh"
+#include "../device/aux_kernels.cuh"
+#include "kernel_table.hpp"
 #include "scene_blob.hpp"
 
 namespace {
@@ -55,6 +56,7 @@ struct DevBuf {
 struct Workspace {
     int device = 0;
     DevBuf staging, accum, out, samples;
+    DevBuf scene_blob[3];  // device image of the owning scene, by blob mode
     unsigned int* d_counter = nullptr;
     unsigned long long* d_segs = nullptr;
     cudaStream_t stream = nullptr;
@@ -76,6 +78,7 @@ struct Workspace {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
         staging.release(); accum.release(); out.release(); samples.release();
+        for (DevBuf& b : scene_blob) b.release();
         if (d_counter) cudaFree(d_counter);
         if (d_segs) cudaFree(d_segs);
         for (cudaEvent_t ev : events) cudaEventDestroy(ev);
@@ -115,6 +118,29 @@ struct Workspace {
         return cudaSuccess;
     }
 };
+
+// The few device attributes the launch logic needs, queried once per device (cudaGetDeviceProperties
+// costs milliseconds; a host application creates a scene per frame).
+struct DeviceInfo {
+    int major = 0, minor = 0, sm_count = 0, max_smem_optin = 0;
+};
+std::mutex g_dev_mutex;
+std::vector<std::pair<int, DeviceInfo>> g_dev_info;
+
+cudaError_t device_info(int device, DeviceInfo* out) {
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    for (const auto& e : g_dev_info)
+        if (e.first == device) { *out = e.second; return cudaSuccess; }
+    DeviceInfo d;
+    cudaError_t e;
+    if ((e = cudaDeviceGetAttribute(&d.major, cudaDevAttrComputeCapabilityMajor, device)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&d.minor, cudaDevAttrComputeCapabilityMinor, device)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess) return e;
+    g_dev_info.emplace_back(device, d);
+    *out = d;
+    return cudaSuccess;
+}
 
 std::mutex g_ws_mutex;
 std::vector<Workspace*> g_ws_cache;
@@ -159,18 +185,50 @@ void ws_release(Workspace* w) {
 
 }  // namespace
 
+// A private copy of the caller's descriptor: blobs for the other traversal modes are built on demand.
+struct OwnedDesc {
+    std::vector<rtiow_item_t> items;
+    std::vector<rtiow_frame_t> frames;
+    std::vector<rtiow_xform_op_t> ops;
+    std::vector<rtiow_material_t> materials;
+    std::vector<rtiow_texture_t> textures;
+    std::vector<float> perlin_vecs;
+    std::vector<uint8_t> perlin_perm;
+    rtiow_scene_desc_t d{};
+    void assign(const rtiow_scene_desc_t* src) {
+        items.assign(src->items, src->items + src->n_items);
+        frames.assign(src->frames, src->frames + src->n_frames);
+        if (src->n_ops) ops.assign(src->ops, src->ops + src->n_ops);
+        if (src->n_materials) materials.assign(src->materials, src->materials + src->n_materials);
+        if (src->n_textures) textures.assign(src->textures, src->textures + src->n_textures);
+        if (src->perlin_vecs) perlin_vecs.assign(src->perlin_vecs, src->perlin_vecs + 768);
+        if (src->perlin_perm) perlin_perm.assign(src->perlin_perm, src->perlin_perm + 768);
+        d = *src;
+        d.items = items.data();
+        d.frames = frames.data();
+        d.ops = ops.empty() ? nullptr : ops.data();
+        d.materials = materials.empty() ? nullptr : materials.data();
+        d.textures = textures.empty() ? nullptr : textures.data();
+        d.perlin_vecs = perlin_vecs.empty() ? nullptr : perlin_vecs.data();
+        d.perlin_perm = perlin_perm.empty() ? nullptr : perlin_perm.data();
+    }
+};
+
 struct rtiow_scene {
     int device = 0;
     int sm_count = 0;
     int max_smem_optin = 0;
-    // [0] = re-indexed Bvh subtrees (default), [1] = the plain reference-order stream
+    OwnedDesc desc;
+    bool uses_perlin = false;
+    // device blobs by rtiow::BlobMode, built and uploaded on first use
     struct Blob {
-        std::vector<unsigned char> host;  // uploaded on first use
+        bool built = false;
+        std::vector<unsigned char> host;
         unsigned char* d = nullptr;
         uint32_t bytes = 0;
         rtiow::BlobLayout lay{};
-    } blobs[2];
-    int traversal = 0;
+    } blobs[3];
+    int traversal = RTIOW_TRAVERSAL_REINDEXED;
     bool has_frames = false;
     uint32_t bg_kind = 0;
     float bg0[3] = {0, 0, 0}, bg1[3] = {0, 0, 0};
@@ -190,27 +248,16 @@ namespace {
 
 using rtiow::KParams;
 
-typedef void (*kernel_fn)(const KParams);
+using rtiow::KernelVariant;
 
-struct Variant {
-    kernel_fn fn;
-    int threads;
-};
-
-template <bool S, bool F>
-Variant pick_threads(uint32_t threads) {
-    switch (threads) {
-        case 128: return {rtiow::render_kernel<S, F, 128, 1>, 128};
-        case 256: return {rtiow::render_kernel<S, F, 256, 1>, 256};
-        case 512: return {rtiow::render_kernel<S, F, 512, 1>, 512};
-        case 1024: return {rtiow::render_kernel<S, F, 1024, 1>, 1024};
-        default: return {rtiow::render_kernel<S, F, 768, 1>, 768};
+rtiow_scene::Blob& blob_of(rtiow_scene* s, rtiow::BlobMode mode) {
+    rtiow_scene::Blob& B = s->blobs[mode];
+    if (!B.built) {
+        B.host = rtiow::build_blob(&s->desc.d, s->uses_perlin, &B.lay, mode);
+        B.bytes = static_cast<uint32_t>(B.host.size());
+        B.built = true;
     }
-}
-
-Variant pick_variant(bool smem, bool frames, uint32_t threads) {
-    if (smem) return frames ? pick_threads<true, true>(threads) : pick_threads<true, false>(threads);
-    return frames ? pick_threads<false, true>(threads) : pick_threads<false, false>(threads);
+    return B;
 }
 
 int ensure_events(rtiow_scene* s, uint32_t n) {
@@ -224,8 +271,11 @@ int ensure_events(rtiow_scene* s, uint32_t n) {
 
 int ensure_uploaded(rtiow_scene* s, rtiow_scene::Blob& B) {
     if (B.d) return RTIOW_OK;
-    CK(cudaMalloc(reinterpret_cast<void**>(&B.d), B.bytes));
-    CK(cudaMemcpy(B.d, B.host.data(), B.bytes, cudaMemcpyHostToDevice));
+    DevBuf& buf = s->ws->scene_blob[&B - s->blobs];  // lives in the (cached) workspace: no cudaMalloc per scene
+    CK(buf.reserve(B.bytes));
+    CK(cudaMemcpyAsync(buf.p, B.host.data(), B.bytes, cudaMemcpyHostToDevice, s->ws->stream));
+    CK(cudaStreamSynchronize(s->ws->stream));  // B.host is pageable; renders may run on other streams
+    B.d = static_cast<unsigned char*>(buf.p);
     return RTIOW_OK;
 }
 
@@ -255,13 +305,22 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     CK(W.staging.reserve(npix64 * s_pass * 16));
     CK(W.accum.reserve(npix64 * 16));
 
-    rtiow_scene::Blob& B = s->blobs[s->traversal];
+    // ---- which blob: REINDEXED means the conservative-test tree when it fits in shared memory, else the
+    // exact-test tree (smaller) when that fits, else the conservative-test tree from global memory
+    const uint32_t smem_cap = static_cast<uint32_t>(s->max_smem_optin) - 1024u;
+    rtiow::BlobMode mode = s->traversal == RTIOW_TRAVERSAL_REFERENCE_ORDER ? rtiow::kBlobReferenceOrder
+                           : (s->traversal == RTIOW_TRAVERSAL_REINDEXED_EXACT ? rtiow::kBlobExact : rtiow::kBlobFast);
+    if (s->traversal == RTIOW_TRAVERSAL_REINDEXED && !s->force_global && blob_of(s, rtiow::kBlobFast).bytes > smem_cap &&
+        blob_of(s, rtiow::kBlobExact).bytes <= smem_cap)
+        mode = rtiow::kBlobExact;
+    rtiow_scene::Blob& B = blob_of(s, mode);
     if (int rc = ensure_uploaded(s, B)) return rc;
-    const bool fits = B.bytes + 1024u <= static_cast<uint32_t>(s->max_smem_optin);
-    const bool smem = fits && !s->force_global;
+    const bool fast = mode == rtiow::kBlobFast && B.lay.n_nodes != 0;
+    const bool smem = B.bytes <= smem_cap && !s->force_global;
     // 0 = automatic: 768 threads (80 registers) per CTA, one CTA per SM; scenes with wrapper frames keep 512
     const uint32_t threads = s->cta_threads ? s->cta_threads : (s->has_frames ? 512u : 768u);
-    const Variant var = pick_variant(smem, s->has_frames, threads);
+    const KernelVariant var = smem ? rtiow::pick_plain_smem(s->has_frames, fast, threads) : rtiow::pick_plain_global(s->has_frames, fast, threads);
+    if (!var.fn) return set_err(RTIOW_ERR_INVALID_ARG, "no kernel instantiation for this cta_threads");
     const size_t dyn_smem = smem ? B.bytes : 0;
     CK(cudaFuncSetAttribute(var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem)));
     int occ = 0;
@@ -280,6 +339,7 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     P.blob_bytes = B.bytes;
     P.off_nodes = B.lay.off_nodes; P.off_frames = B.lay.off_frames; P.off_ops = B.lay.off_ops; P.off_mats = B.lay.off_mats;
     P.off_tex = B.lay.off_tex; P.off_pvecs = B.lay.off_pvecs; P.off_pperm = B.lay.off_pperm;
+    P.off_fnodes = B.lay.off_fnodes;
     std::memcpy(P.cam, cam, sizeof(float) * 21);
     P.nx = nx; P.ny = ny; P.row_begin = r0; P.n_rows = n_rows; P.row_step = step;
     P.npix = npix; P.n_groups = n_groups;
@@ -338,6 +398,8 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     s->stats.block = static_cast<uint32_t>(var.threads);
     s->stats.dyn_smem_bytes = static_cast<uint32_t>(dyn_smem);
     s->stats.regs_per_thread = static_cast<uint32_t>(fa.numRegs);
+    s->stats.traversal = static_cast<uint32_t>(mode == rtiow::kBlobFast ? RTIOW_TRAVERSAL_REINDEXED
+                                               : (mode == rtiow::kBlobExact ? RTIOW_TRAVERSAL_REINDEXED_EXACT : RTIOW_TRAVERSAL_REFERENCE_ORDER));
     return RTIOW_OK;
 }
 
@@ -372,16 +434,16 @@ int rtiow_b200_scene_create(const rtiow_scene_desc_t* d, int device, rtiow_scene
                                                 cudaGetErrorString(e));
     if (device < 0 || device >= n_dev) return set_err(RTIOW_ERR_INVALID_ARG, "device ordinal out of range");
     CK(cudaSetDevice(device));
-    cudaDeviceProp prop{};
-    CK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10)
-        return set_err(RTIOW_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+    DeviceInfo info{};
+    CK(device_info(device, &info));
+    if (info.major != 10)
+        return set_err(RTIOW_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(info.major) + std::to_string(info.minor) +
                                                 "; this library carries sm_100a code only");
 
     auto s = new rtiow_scene();
     s->device = device;
-    s->sm_count = prop.multiProcessorCount;
-    s->max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    s->sm_count = info.sm_count;
+    s->max_smem_optin = info.max_smem_optin;
     s->has_frames = has_frames;
     s->bg_kind = d->background_kind;
     std::memcpy(s->bg0, d->background_c0, 12);
@@ -391,12 +453,8 @@ int rtiow_b200_scene_create(const rtiow_scene_desc_t* d, int device, rtiow_scene
         rtiow_b200_scene_destroy(s);
         return set_err(RTIOW_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(ce));
     };
-    // ---- build the device blobs: items | accel nodes | frames | ops | materials | textures | perlin
-    for (int v = 0; v < 2; ++v) {
-        rtiow_scene::Blob& B = s->blobs[v];
-        B.host = rtiow::build_blob(d, uses_perlin, &B.lay, v == 0);
-        B.bytes = static_cast<uint32_t>(B.host.size());
-    }
+    s->desc.assign(d);
+    s->uses_perlin = uses_perlin;
     s->ws = ws_acquire(device, &e);
     if (!s->ws) return fail(e, "workspace");
 
@@ -404,11 +462,15 @@ int rtiow_b200_scene_create(const rtiow_scene_desc_t* d, int device, rtiow_scene
     if (const char* env = std::getenv("RTIOW_B200_CTAS_PER_SM")) s->ctas_per_sm = static_cast<uint32_t>(std::atoi(env));
     if (const char* env = std::getenv("RTIOW_B200_STAGING_MIB")) s->staging_mib = static_cast<uint32_t>(std::atoi(env));
     if (const char* env = std::getenv("RTIOW_B200_FORCE_GLOBAL")) s->force_global = std::atoi(env) != 0;
-    if (const char* env = std::getenv("RTIOW_B200_TRAVERSAL")) s->traversal = std::atoi(env) != 0 ? 1 : 0;
+    if (const char* env = std::getenv("RTIOW_B200_TRAVERSAL")) s->traversal = std::min(2, std::max(0, std::atoi(env)));
     if (const char* env = std::getenv("RTIOW_B200_SAMPLE_CHUNK")) s->sample_chunk = static_cast<uint32_t>(std::max(0, std::atoi(env)));
-    if (int rc = ensure_uploaded(s, s->blobs[s->traversal])) {
-        rtiow_b200_scene_destroy(s);
-        return rc;
+    {   // build + upload the blob of the selected traversal now, so that render calls only launch
+        const rtiow::BlobMode mode = s->traversal == RTIOW_TRAVERSAL_REFERENCE_ORDER ? rtiow::kBlobReferenceOrder
+                                     : (s->traversal == RTIOW_TRAVERSAL_REINDEXED_EXACT ? rtiow::kBlobExact : rtiow::kBlobFast);
+        if (int rc = ensure_uploaded(s, blob_of(s, mode))) {
+            rtiow_b200_scene_destroy(s);
+            return rc;
+        }
     }
     *out = s;
     return RTIOW_OK;
@@ -429,17 +491,15 @@ void rtiow_b200_release_cached_memory(void) {
 void rtiow_b200_scene_destroy(rtiow_scene_t* s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    ws_release(s->ws);  // synchronises the scene's stream first
-    for (auto& B : s->blobs)
-        if (B.d) cudaFree(B.d);
+    ws_release(s->ws);  // synchronises the scene's stream first; the blobs' device memory stays with the workspace
     delete s;
 }
 
 int rtiow_b200_set_tuning(rtiow_scene_t* s, uint32_t cta_threads, uint32_t ctas_per_sm, uint32_t staging_mib, int force_global) {
     if (!s) return set_err(RTIOW_ERR_INVALID_ARG, "null scene");
     if (cta_threads) {
-        if (cta_threads != 128 && cta_threads != 256 && cta_threads != 512 && cta_threads != 768 && cta_threads != 1024)
-            return set_err(RTIOW_ERR_INVALID_ARG, "cta_threads must be 128, 256, 512, 768 or 1024");
+        if (cta_threads != 256 && cta_threads != 512 && cta_threads != 768)
+            return set_err(RTIOW_ERR_INVALID_ARG, "cta_threads must be 256, 512 or 768");
     }
     s->cta_threads = cta_threads;
     s->ctas_per_sm = ctas_per_sm;
@@ -450,7 +510,7 @@ int rtiow_b200_set_tuning(rtiow_scene_t* s, uint32_t cta_threads, uint32_t ctas_
 
 int rtiow_b200_set_traversal(rtiow_scene_t* s, int mode) {
     if (!s) return set_err(RTIOW_ERR_INVALID_ARG, "null scene");
-    if (mode != RTIOW_TRAVERSAL_REINDEXED && mode != RTIOW_TRAVERSAL_REFERENCE_ORDER)
+    if (mode != RTIOW_TRAVERSAL_REINDEXED && mode != RTIOW_TRAVERSAL_REFERENCE_ORDER && mode != RTIOW_TRAVERSAL_REINDEXED_EXACT)
         return set_err(RTIOW_ERR_INVALID_ARG, "unknown traversal mode");
     s->traversal = mode;
     return RTIOW_OK;

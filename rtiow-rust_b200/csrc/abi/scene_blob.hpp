@@ -122,8 +122,12 @@ inline int validate_desc(const rtiow_scene_desc_t* d, bool* has_frames, bool* us
 }
 
 
+// How Bvh subtrees are laid out for the device (rtiow_b200.h RTIOW_TRAVERSAL_*).
+enum BlobMode { kBlobFast = 0, kBlobReferenceOrder = 1, kBlobExact = 2 };
+
 struct BlobLayout {
     uint32_t off_nodes, off_frames, off_ops, off_mats, off_tex, off_pvecs, off_pperm;
+    uint32_t off_fnodes;
     uint32_t n_items, n_nodes, n_accel, accel_depth;
 };
 
@@ -139,6 +143,7 @@ namespace blob_detail {
 struct Compactor {
     const rtiow_scene_desc_t* d;
     bool enable_accel;
+    bool keep_leaf_boxes;  // kBlobFast: every leaf's own BBOX item stays in front of its primitives
     std::vector<rtiow_item_t> out;
     std::vector<AccelNode> nodes;
     uint32_t n_accel = 0;
@@ -184,6 +189,11 @@ struct Compactor {
                         AccelLeaf l{};
                         std::memcpy(l.mn, d->items[rl.box].a, 12);
                         std::memcpy(l.mx, d->items[rl.box].b, 12);
+                        if (keep_leaf_boxes) {
+                            rtiow_item_t box = d->items[rl.box];
+                            box.a_w = RTIOW_ITEM_BBOX | (static_cast<uint32_t>(out.size() + 1 + (rl.end - rl.first)) << 4);
+                            out.push_back(box);
+                        }
                         l.first = static_cast<uint32_t>(out.size());
                         l.count = rl.end - rl.first;
                         for (uint32_t j = rl.first; j < rl.end; ++j) out.push_back(d->items[j]);
@@ -225,7 +235,8 @@ struct Compactor {
 // every section starts on a 128-byte boundary so the whole blob can be moved with 128 B-granular
 // TMA bulk copies.
 inline std::vector<unsigned char> build_blob(const rtiow_scene_desc_t* d, bool uses_perlin, BlobLayout* lay,
-                                             bool enable_accel = true) {
+                                             BlobMode mode = kBlobFast) {
+    const bool enable_accel = mode != kBlobReferenceOrder;
     std::vector<unsigned char> blob;
     auto align_up = [](size_t v) { return (v + 127u) / 128u * 128u; };
     auto append = [&](const void* src, size_t bytes) -> uint32_t {
@@ -234,16 +245,25 @@ inline std::vector<unsigned char> build_blob(const rtiow_scene_desc_t* d, bool u
         if (bytes) std::memcpy(blob.data() + off, src, bytes);
         return static_cast<uint32_t>(off);
     };
-    blob_detail::Compactor cp{d, enable_accel, {}, {}};
+    blob_detail::Compactor cp{d, enable_accel, mode == kBlobFast, {}, {}};
     try {
         cp.run(0, d->n_items);
     } catch (int) {  // odd nesting: ship the stream as it is
-        cp = blob_detail::Compactor{d, false, {}, {}};
+        cp = blob_detail::Compactor{d, false, false, {}, {}};
         cp.out.assign(d->items, d->items + d->n_items);
     }
     append(cp.out.data(), sizeof(rtiow_item_t) * cp.out.size());
     lay->n_items = static_cast<uint32_t>(cp.out.size());
-    lay->off_nodes = append(cp.nodes.data(), sizeof(AccelNode) * cp.nodes.size());
+    if (mode == kBlobFast) {
+        std::vector<FastNode> fast;
+        fast.reserve(cp.nodes.size());
+        for (const AccelNode& n : cp.nodes) fast.push_back(to_fast_node(n));
+        lay->off_fnodes = append(fast.data(), sizeof(FastNode) * fast.size());
+        lay->off_nodes = lay->off_fnodes;
+    } else {
+        lay->off_nodes = append(cp.nodes.data(), sizeof(AccelNode) * cp.nodes.size());
+        lay->off_fnodes = 0;
+    }
     lay->n_nodes = static_cast<uint32_t>(cp.nodes.size());
     lay->n_accel = cp.n_accel;
     lay->accel_depth = static_cast<uint32_t>(cp.max_depth);

@@ -29,6 +29,7 @@ struct KParams {
     const unsigned char* blob;  // device scene blob; items start at offset 0
     uint32_t blob_bytes;
     uint32_t off_nodes, off_frames, off_ops, off_mats, off_tex, off_pvecs, off_pperm;
+    uint32_t off_fnodes;        // conservative-test nodes (accel_build.hpp FastNode); 0 = none
     float cam[21];              // rtiow_camera_t
     uint32_t nx, ny, row_begin, n_rows, row_step;  // rows row_begin, row_begin + row_step, ... (n_rows of them)
     uint32_t s_begin, s_count;  // samples [s_begin, s_begin + s_count) of every pixel in this pass
@@ -84,7 +85,7 @@ struct MemGlobal {
 template <class Mem>
 struct SceneT {
     Mem m;
-    uint32_t off_nodes, off_frames, off_ops, off_mats, off_tex, off_pvecs, off_pperm;
+    uint32_t off_nodes, off_frames, off_ops, off_mats, off_tex, off_pvecs, off_pperm, off_fnodes;
     RT_HD float4 item_a(uint32_t i) const { return m.ld4(32u * i); }
     RT_HD float4 item_b(uint32_t i) const { return m.ld4(32u * i + 16u); }
     RT_HD float4 node_q(uint32_t n, uint32_t q) const { return m.ld4(off_nodes + 64u * n + 16u * q); }
@@ -102,6 +103,7 @@ RT_HD SceneT<Mem> scene_views(Mem m, const KParams& P) {
     sc.m = m;
     sc.off_nodes = P.off_nodes; sc.off_frames = P.off_frames; sc.off_ops = P.off_ops; sc.off_mats = P.off_mats;
     sc.off_tex = P.off_tex; sc.off_pvecs = P.off_pvecs; sc.off_pperm = P.off_pperm;
+    sc.off_fnodes = P.off_fnodes;
     return sc;
 }
 
@@ -118,6 +120,18 @@ struct PathState {
     V3 ro, rd, strength;
     float rtime;
     Rng rng;
+};
+
+// What hit_top needs to know about the path besides the ray it is tracing, read on demand
+// (wrapper frames need the ray's time, a ConstantMedium its random numbers): a view, so that a
+// caller can keep those fields wherever it likes.
+struct PathStateView {
+    const PathState* st;
+    RT_HD V3 ro() const { return st->ro; }
+    RT_HD V3 rd() const { return st->rd; }
+    RT_HD float rtime() const { return st->rtime; }
+    RT_HD Rng rng() const { return st->rng; }
+    RT_HD uint32_t bounce() const { return st->bounce; }
 };
 
 RT_HD void apply_op_ray(const float4 op, V3& o, V3& d, float time) {
@@ -202,15 +216,15 @@ RT_HD bool rect_hit_t(V3 o, V3 d, uint32_t axis, float4 ia, float4 ib, float t_l
 // Any primitive item against a ray (o, d) that is already in frame `cur_frame` (whose chain has
 // `cur_nops` ops, a prefix of the item's own chain): the item's remaining wrappers are applied
 // first, exactly like the nested Object::hit calls.
-template <class Mem>
-RT_HD bool prim_hit_t(const SceneT<Mem>& sc, float4 ia, float4 ib, V3 o, V3 d, float time, uint32_t cur_frame,
+template <class Mem, class Path>
+RT_HD bool prim_hit_t(const SceneT<Mem>& sc, float4 ia, float4 ib, V3 o, V3 d, const Path& path, uint32_t cur_frame,
                       uint32_t cur_nops, float t_lo, float t_hi, float& t_out) {
     const uint32_t kind = f2u(ia.w) & 15u;
     const uint32_t frame = f2u(ia.w) >> 4;
     const uint32_t flags = f2u(ib.w) >> 24;
     if (frame != cur_frame) {
         const uint2 fr = sc.frame(frame);
-        const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * (fr.x + cur_nops), fr.y - cur_nops, o, d, time);
+        const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * (fr.x + cur_nops), fr.y - cur_nops, o, d, path.rtime());
         o = r.o;
         d = r.d;
     }
@@ -371,6 +385,10 @@ struct Trav {
     uint32_t best;     // winning item so far
     V3 fo, fd, inv;    // the ray in the current BBOX frame and its 1/d (aabb.rs:19)
     uint32_t f_id, f_nops;
+    // conservative box test of the re-indexed subtrees (kFast traversal only; see trav_fast_setup)
+    V3 fc;             // n = fma(plane, inv, fc)
+    uint32_t nbx, nby, nbz;  // blob offsets of the ray's near/far-ordered plane quads of node 0
+    float ek2, omek;   // slack of a node with coordinate magnitude m: fma(m, ek2, omek); ek2 = +inf: test nothing
 };
 // The per-lane stack of (link, entry t) lives apart from Trav: a dynamically indexed array sits in
 // local memory, and must not drag the scalars above there with it.
@@ -383,17 +401,18 @@ RT_HD bool trav_in_node(const Trav& tr) { return tr.cur < kLinkNone; }
 RT_HD bool trav_in_leaf(const Trav& tr) { return (tr.cur & kLinkLeafBit) != 0u; }
 RT_HD bool trav_done(const Trav& tr) { return tr.cur == kLinkNone && tr.i == kStreamEnd; }
 
-RT_HD void trav_begin(const PathState& st, Trav& tr) {
+RT_HD void trav_begin(V3 ro, V3 rd, Trav& tr) {
     tr.i = 0u;
     tr.cur = kLinkNone;
     tr.sp = 0;
     tr.best_t = kF32Max;
     tr.best = kNoHit;
-    tr.fo = st.ro;
-    tr.fd = st.rd;
-    tr.inv = mk(1.f / st.rd.x, 1.f / st.rd.y, 1.f / st.rd.z);
+    tr.fo = ro;
+    tr.fd = rd;
+    tr.inv = mk(1.f / rd.x, 1.f / rd.y, 1.f / rd.z);
     tr.f_id = 0u;
     tr.f_nops = 0u;
+    tr.fc = splat(0.f); tr.nbx = tr.nby = tr.nbz = 0u; tr.ek2 = 0.f; tr.omek = 0.f;
 }
 
 // Pop the next link worth visiting: entries the current best already beats are dropped (their box
@@ -438,24 +457,125 @@ RT_HD void trav_node_step(const SceneT<Mem>& sc, Trav& tr, TravStack& stk) {  //
     }
 }
 
-template <class Mem>
-RT_HD void trav_leaf_test(const SceneT<Mem>& sc, float time, Trav& tr, uint32_t link) {
+template <class Mem, class Path>
+RT_HD void trav_leaf_test(const SceneT<Mem>& sc, const Path& path, Trav& tr, uint32_t link) {
     const uint32_t first = link & 0x00ffffffu, count = (link >> 24) & 0x7fu;
     for (uint32_t j = first; j < first + count; ++j) {
         const float4 ia = sc.item_a(j), ib = sc.item_b(j);
         const float t_hi = (tr.best != kNoHit && j < tr.best) ? next_up_pos(tr.best_t) : tr.best_t;
         float t;
-        if (prim_hit_t(sc, ia, ib, tr.fo, tr.fd, time, tr.f_id, tr.f_nops, kNear, t_hi, t)) {
+        if (prim_hit_t(sc, ia, ib, tr.fo, tr.fd, path, tr.f_id, tr.f_nops, kNear, t_hi, t)) {
             tr.best_t = t;
             tr.best = j;
         }
     }
 }
-template <class Mem>
-RT_HD void trav_leaf_step(const SceneT<Mem>& sc, float time, Trav& tr, const TravStack& stk) {  // requires trav_in_leaf(tr)
-    trav_leaf_test(sc, time, tr, tr.cur);
+template <class Mem, class Path>
+RT_HD void trav_leaf_step(const SceneT<Mem>& sc, const Path& path, Trav& tr, const TravStack& stk) {  // requires trav_in_leaf(tr)
+    trav_leaf_test(sc, path, tr, tr.cur);
     trav_pop(tr, stk);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Conservative box tests for the INNER boxes of a re-indexed subtree.
+//
+// An inner box only culls: the image cannot change as long as the test never rejects a box whose
+// leaf below would pass the reference's Aabb::hit.  So inner boxes (and, as a first filter, leaf
+// boxes) are tested with n = fma(plane, 1/d, -(o * 1/d)) on planes that the node stores already
+// ordered near/far for the ray's direction signs — 6 FFMA + 4 min/max per box instead of
+// 6 FADD + 6 FMUL + 6 FSEL + 4 min/max — and accepted when `end - start > -e2`, where e2 bounds
+// twice the difference to the reference's (plane - o) * (1/d):
+//     |fl((p - o) * i) - fl(fma(p, i, -fl(o * i)))| <= 4 * 2^-24 * (|p| + |o|) * |i|
+// (one rounding of p - o, of the product, of o * i and of the fma, each relative to a quantity
+// bounded by (|p| + |o|) * |i|).  e2 = 2^-19 * (m + max|o|) * max|i| is 4x that bound, m being the
+// largest |coordinate| in the node.  Leaves then run the reference's exact Aabb::hit on their own
+// box before any primitive test (trav_leaf_step_fast), so every accepted hit went through exactly
+// the reference's tests.  Axes on which 1/d is not a moderate finite number (d = 0, denormal, inf,
+// NaN; |o| huge) switch the ray to "test nothing": e2 = +inf.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kFastNodeBytes = 112u;  // accel_build.hpp FastNode
+
+RT_HD float rt_fma(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
+RT_HD float rt_max3(float a, float b, float c) { return rt_max(rt_max(a, b), c); }
+RT_HD float rt_min3(float a, float b, float c) { return rt_min(rt_min(a, b), c); }
+
+// Call after tr.fo / tr.fd / tr.inv are set (trav_begin, SET_FRAME).
+template <class Mem>
+RT_HD void trav_fast_setup(const SceneT<Mem>& sc, Trav& tr) {
+    const float lo = 7.8886090522101181e-31f, hi = 1.2676506002282294e+30f;  // 2^-100, 2^100
+    const float ax = fabsf(tr.inv.x), ay = fabsf(tr.inv.y), az = fabsf(tr.inv.z);
+    const float om = rt_max3(fabsf(tr.fo.x), fabsf(tr.fo.y), fabsf(tr.fo.z));
+    const bool ok = ax > lo && ax < hi && ay > lo && ay < hi && az > lo && az < hi && om < 67108864.f;  // NaN fails
+    tr.nbx = sc.off_fnodes + (tr.inv.x < 0.f ? 16u : 0u);
+    tr.nby = sc.off_fnodes + 32u + (tr.inv.y < 0.f ? 16u : 0u);
+    tr.nbz = sc.off_fnodes + 64u + (tr.inv.z < 0.f ? 16u : 0u);
+    if (ok) {
+        tr.fc = mk(-(tr.fo.x * tr.inv.x), -(tr.fo.y * tr.inv.y), -(tr.fo.z * tr.inv.z));
+        tr.ek2 = 1.9073486328125e-06f * rt_max3(ax, ay, az);  // 2^-19
+        tr.omek = om * tr.ek2;
+    } else {  // every fast test passes (0 * plane + 0 = 0 on all axes, slack +inf); exact tests recompute 1/d
+        tr.inv = splat(0.f);
+        tr.fc = splat(0.f);
+        tr.ek2 = u2f(0x7f800000u);
+        tr.omek = 0.f;
+    }
+}
+
+// 1/d for the reference's Aabb::hit (aabb.rs:19): tr.inv, unless the fast setup had to blank it.
+template <bool kFast>
+RT_HD V3 trav_exact_inv(const Trav& tr) {
+    if (kFast && !(tr.ek2 < u2f(0x7f800000u))) return mk(1.f / tr.fd.x, 1.f / tr.fd.y, 1.f / tr.fd.z);
+    return tr.inv;
+}
+
+template <class Mem>
+RT_HD void trav_node_step_fast(const SceneT<Mem>& sc, Trav& tr, TravStack& stk) {  // requires trav_in_node(tr)
+    const uint32_t nb = tr.cur * kFastNodeBytes;
+    const float4 X = sc.m.ld4(tr.nbx + nb), Y = sc.m.ld4(tr.nby + nb), Z = sc.m.ld4(tr.nbz + nb);  // {near0, far0, near1, far1}
+    const float4 L = sc.m.ld4(sc.off_fnodes + 96u + nb);                                            // {link0, link1, m, -}
+    const V3 iv = tr.inv;
+    const float s0 = rt_max(kNear, rt_max3(rt_fma(X.x, iv.x, tr.fc.x), rt_fma(Y.x, iv.y, tr.fc.y), rt_fma(Z.x, iv.z, tr.fc.z)));
+    const float e0 = rt_min(tr.best_t, rt_min3(rt_fma(X.y, iv.x, tr.fc.x), rt_fma(Y.y, iv.y, tr.fc.y), rt_fma(Z.y, iv.z, tr.fc.z)));
+    const float s1 = rt_max(kNear, rt_max3(rt_fma(X.z, iv.x, tr.fc.x), rt_fma(Y.z, iv.y, tr.fc.y), rt_fma(Z.z, iv.z, tr.fc.z)));
+    const float e1 = rt_min(tr.best_t, rt_min3(rt_fma(X.w, iv.x, tr.fc.x), rt_fma(Y.w, iv.y, tr.fc.y), rt_fma(Z.w, iv.z, tr.fc.z)));
+    const float e2 = rt_fma(L.z, tr.ek2, tr.omek);
+    const uint32_t l0 = f2u(L.x), l1 = f2u(L.y);
+    const bool h0 = (e0 - s0) > -e2;
+    const bool h1 = (e1 - s1) > -e2 && l1 != kLinkNone;
+    if (h0 && h1) {
+        const bool first0 = s0 <= s1;
+        stk.link[tr.sp] = first0 ? l1 : l0;
+        stk.t[tr.sp] = (first0 ? s1 : s0) - e2;  // popped only while best_t > this: still conservative
+        ++tr.sp;
+        tr.cur = first0 ? l0 : l1;
+    } else if (h0 || h1) {
+        tr.cur = h0 ? l0 : l1;
+    } else {
+        trav_pop(tr, stk);
+    }
+}
+
+// A leaf of the fast tree: the reference's Aabb::hit (aabb.rs:18-29) on the leaf's own box — the
+// BBOX item kept in front of its primitives — and then the primitives.
+template <class Mem, class Path>
+RT_HD void trav_leaf_step_fast(const SceneT<Mem>& sc, const Path& path, Trav& tr, const TravStack& stk) {  // requires trav_in_leaf(tr)
+    const uint32_t first = tr.cur & 0x00ffffffu;
+    const float4 mn = sc.item_a(first - 1u), mx = sc.item_b(first - 1u);
+    float start;
+    if (slab_test(mn, mx, tr.fo, trav_exact_inv<true>(tr), tr.best_t, start)) trav_leaf_test(sc, path, tr, tr.cur);
+    trav_pop(tr, stk);
+}
+
+struct TimeOnlyView {
+    float time;
+    RT_HD float rtime() const { return time; }
+};
 
 // ConstantMedium::hit (object.rs:543-575); item i is the medium, item i+1 its boundary primitive.
 struct BestHit {
@@ -478,8 +598,9 @@ RT_HD_NOINLINE BestHit medium_hit(const SceneT<Mem> sc, Rng rng, uint32_t bounce
     }
     const float4 ba = sc.item_a(i + 1u), bb = sc.item_b(i + 1u);
     float t1, t2;
-    if (prim_hit_t(sc, ba, bb, mo, md, time, mframe, m_nops, kF32Min, kF32Max, t1) &&
-        prim_hit_t(sc, ba, bb, mo, md, time, mframe, m_nops, t1 + 0.0001f, kF32Max, t2)) {
+    const TimeOnlyView tv{time};
+    if (prim_hit_t(sc, ba, bb, mo, md, tv, mframe, m_nops, kF32Min, kF32Max, t1) &&
+        prim_hit_t(sc, ba, bb, mo, md, tv, mframe, m_nops, t1 + 0.0001f, kF32Max, t2)) {
         t1 = rt_max(t1, kNear);
         t2 = rt_min(t2, best_t);
         if (!(t1 >= t2)) {
@@ -502,8 +623,8 @@ RT_HD_NOINLINE BestHit medium_hit(const SceneT<Mem> sc, Rng rng, uint32_t bounce
 // ------------------------------------------------------------------------------------------------
 // Interprets stream items from tr.i until a re-indexed subtree starts (tr.cur = its root) or the
 // stream ends (tr.i = kStreamEnd).
-template <bool kFrames, class Mem>
-RT_HD void trav_stream(const SceneT<Mem>& sc, const PathState& st, Trav& tr) {
+template <bool kFrames, bool kFast, class Mem, class Path>
+RT_HD void trav_stream(const SceneT<Mem>& sc, const Path& path, Trav& tr) {
     // the last wrapped primitive's frame: the six rects of a rotated prism share one chain
     uint32_t pf_id = tr.f_id;
     V3 po = tr.fo, pd = tr.fd;
@@ -519,26 +640,26 @@ RT_HD void trav_stream(const SceneT<Mem>& sc, const PathState& st, Trav& tr) {
         } else if (kind == IT_BBOX) {  // Aabb::hit  aabb.rs:18-29
             const float4 ib = sc.item_b(i);
             float start;
-            i = slab_test(ia, ib, tr.fo, tr.inv, tr.best_t, start) ? i + 1u : (f2u(ia.w) >> 4);
+            i = slab_test(ia, ib, tr.fo, trav_exact_inv<kFast>(tr), tr.best_t, start) ? i + 1u : (f2u(ia.w) >> 4);
         } else if (kind == IT_SPHERE || kind == IT_RECT) {
             const float4 ib = sc.item_b(i);
             const uint32_t frame = f2u(ia.w) >> 4;
             if (frame != tr.f_id && frame != pf_id) {
                 const uint2 fr = sc.frame(frame);
-                const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * (fr.x + tr.f_nops), fr.y - tr.f_nops, tr.fo, tr.fd, st.rtime);
+                const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * (fr.x + tr.f_nops), fr.y - tr.f_nops, tr.fo, tr.fd, path.rtime());
                 po = r.o;
                 pd = r.d;
                 pf_id = frame;
             }
             const bool own = frame != tr.f_id;
             float t;
-            if (prim_hit_t(sc, ia, ib, own ? po : tr.fo, own ? pd : tr.fd, st.rtime, frame, 0u, kNear, tr.best_t, t)) {
+            if (prim_hit_t(sc, ia, ib, own ? po : tr.fo, own ? pd : tr.fd, path, frame, 0u, kNear, tr.best_t, t)) {
                 tr.best_t = t;  // nearest = rec.t (lib.rs:42) / t_range.end = h.t (bvh.rs:98-100, object.rs:404-406)
                 tr.best = i;
             }
             i += 1u;
         } else if (kind == IT_MEDIUM) {
-            const BestHit h = medium_hit(sc, st.rng, st.bounce, st.rtime, i, tr.fo, tr.fd, tr.f_id, tr.f_nops, tr.best_t, tr.best);
+            const BestHit h = medium_hit(sc, path.rng(), path.bounce(), path.rtime(), i, tr.fo, tr.fd, tr.f_id, tr.f_nops, tr.best_t, tr.best);
             tr.best_t = h.t;
             tr.best = h.item;
             i += 2u;
@@ -546,11 +667,12 @@ RT_HD void trav_stream(const SceneT<Mem>& sc, const PathState& st, Trav& tr) {
             if (kFrames) {
                 tr.f_id = f2u(ia.w) >> 4;
                 const uint2 fr = sc.frame(tr.f_id);
-                const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * fr.x, fr.y, st.ro, st.rd, st.rtime);
+                const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * fr.x, fr.y, path.ro(), path.rd(), path.rtime());
                 tr.fo = r.o;
                 tr.fd = r.d;
                 tr.f_nops = fr.y;
                 tr.inv = mk(1.f / tr.fd.x, 1.f / tr.fd.y, 1.f / tr.fd.z);
+                if (kFast) trav_fast_setup(sc, tr);
                 pf_id = tr.f_id;
                 po = tr.fo;
                 pd = tr.fd;
@@ -568,16 +690,23 @@ RT_HD void trav_stream(const SceneT<Mem>& sc, const PathState& st, Trav& tr) {
 // World::hit_top: the steps above run back to back for one ray.  Returns the index of the winning
 // item (kNoHit if none) and its t.
 // ------------------------------------------------------------------------------------------------
-template <bool kFrames, class Mem>
+template <bool kFrames, bool kFast, class Mem>
 RT_HD uint32_t hit_top_stream(const SceneT<Mem>& sc, const PathState& st, float& best_t_out) {
     Trav tr;
     TravStack stk;
-    trav_begin(st, tr);
+    const PathStateView path{&st};
+    trav_begin(st.ro, st.rd, tr);
+    if (kFast) trav_fast_setup(sc, tr);
     for (;;) {
-        trav_stream<kFrames>(sc, st, tr);
+        trav_stream<kFrames, kFast>(sc, path, tr);
         while (tr.cur != kLinkNone) {  // "while-while": lanes stay together in the cheap node loop
-            while (trav_in_node(tr)) trav_node_step(sc, tr, stk);
-            if (trav_in_leaf(tr)) trav_leaf_step(sc, st.rtime, tr, stk);
+            if (kFast) {
+                while (trav_in_node(tr)) trav_node_step_fast(sc, tr, stk);
+                if (trav_in_leaf(tr)) trav_leaf_step_fast(sc, path, tr, stk);
+            } else {
+                while (trav_in_node(tr)) trav_node_step(sc, tr, stk);
+                if (trav_in_leaf(tr)) trav_leaf_step(sc, path, tr, stk);
+            }
         }
         if (tr.i == kStreamEnd) break;
     }

@@ -1,0 +1,22 @@
+// Included by plain_smem.cu / plain_global.cu with RTIOW_PLAIN_SMEM and RTIOW_PLAIN_NAME defined.
+#include "../abi/kernel_table.hpp"
+#include "../device/render_kernel.cuh"
+
+namespace rtiow {
+namespace {
+template <bool F, bool Q>
+KernelVariant by_threads(uint32_t threads) {
+    switch (threads) {
+        case 256: return {render_kernel<RTIOW_PLAIN_SMEM, F, Q, 256, 1>, 256};
+        case 512: return {render_kernel<RTIOW_PLAIN_SMEM, F, Q, 512, 1>, 512};
+        case 768: return {render_kernel<RTIOW_PLAIN_SMEM, F, Q, 768, 1>, 768};
+        default: return {nullptr, 0};
+    }
+}
+}  // namespace
+
+KernelVariant RTIOW_PLAIN_NAME(bool frames, bool fast, uint32_t threads) {
+    if (frames) return fast ? by_threads<true, true>(threads) : by_threads<true, false>(threads);
+    return fast ? by_threads<false, true>(threads) : by_threads<false, false>(threads);
+}
+}  // namespace rtiow

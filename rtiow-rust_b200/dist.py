@@ -115,11 +115,11 @@ def par_cast_e2e(nx, ny, ns, camera, world, bufs, host_out, seed=api.DEFAULT_SEE
     sh = bufs.shard
     dev = bufs.frame.device.index or 0
     world.upload_fresh(dev)
-    h2d = world.stats(dev)["scene_bytes"] + C.sizeof(N.CameraRec)
     if sh.world_size == 1:
         api._check(N.abi().rtiow_b200_render(world.gpu(dev), C.byref(camera.rec), nx, ny, ns, seed, host_out.ctypes.data))
-        return h2d, host_out.nbytes
+        return world.scene_bytes(dev) + C.sizeof(N.CameraRec), host_out.nbytes
     render_sharded_device(nx, ny, ns, camera, world, bufs, seed=seed)
+    h2d = world.scene_bytes(dev) + C.sizeof(N.CameraRec)
     d2h = 0
     if sh.rank == 0:
         host_out.copy_(bufs.frame, non_blocking=True)

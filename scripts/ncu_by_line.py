@@ -16,8 +16,8 @@ src_csv, so, kname = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
-cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", cubin], capture_output=True, text=True).stdout
+dis = "".join(subprocess.run(["nvdisasm", "-g", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+              for f in sorted(os.listdir(tmp)) if f.endswith(".cubin"))  # one cubin per translation unit
 lines, cur, on = [], None, False
 for l in dis.splitlines():
     if l.startswith(".text."):

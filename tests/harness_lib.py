@@ -19,7 +19,8 @@ def lib():
                         (("device", "path_logic.cuh"), ("device", "rt_math.cuh"), ("abi", "scene_blob.hpp"), ("abi", "accel_build.hpp"))]
         if not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps):
             os.makedirs(os.path.dirname(_SO), exist_ok=True)
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", _SO, src])
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fvisibility=hidden", "-Wl,-Bsymbolic",
+                                   "-shared", "-o", _SO, src])
         _lib = C.CDLL(_SO)
         _lib.harness_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
                                         C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32]

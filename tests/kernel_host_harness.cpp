@@ -12,8 +12,10 @@
 #include "../rtiow-rust_b200/csrc/abi/scene_blob.hpp"
 #include "../rtiow-rust_b200/csrc/device/path_logic.cuh"
 
-// accel != 0: the re-indexed (SAH, ordered) traversal the device uses; 0: the plain reference-order stream.
-extern "C" int harness_render(const rtiow_scene_desc_t* desc, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny,
+// accel = 1: the re-indexed (SAH, ordered) traversal with conservative inner box tests that the device
+// uses by default; 2: the same tree with the reference's exact box test at every node; 0: the plain
+// reference-order stream.
+extern "C" __attribute__((visibility("default"))) int harness_render(const rtiow_scene_desc_t* desc, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny,
                               uint32_t ns, uint64_t seed, uint32_t row_begin, uint32_t row_end, float* out_rgb,
                               float* out_samples, int accel, uint32_t* layout_out, uint32_t row_step) {
     using namespace rtiow;
@@ -21,13 +23,14 @@ extern "C" int harness_render(const rtiow_scene_desc_t* desc, const rtiow_camera
     std::string msg;
     if (int rc = validate_desc(desc, &has_frames, &uses_perlin, &msg)) return rc;
     BlobLayout lay{};
-    const std::vector<unsigned char> blob = build_blob(desc, uses_perlin, &lay, accel != 0);
+    const std::vector<unsigned char> blob = build_blob(desc, uses_perlin, &lay, accel == 1 ? kBlobFast : (accel == 2 ? kBlobExact : kBlobReferenceOrder));
     if (layout_out) { layout_out[0] = lay.n_items; layout_out[1] = lay.n_nodes; layout_out[2] = lay.n_accel; layout_out[3] = lay.accel_depth; }
     KParams P{};
     P.blob = blob.data();
     P.blob_bytes = static_cast<uint32_t>(blob.size());
     P.off_nodes = lay.off_nodes; P.off_frames = lay.off_frames; P.off_ops = lay.off_ops; P.off_mats = lay.off_mats; P.off_tex = lay.off_tex;
-    P.off_pvecs = lay.off_pvecs; P.off_pperm = lay.off_pperm;
+    P.off_pvecs = lay.off_pvecs; P.off_pperm = lay.off_pperm; P.off_fnodes = lay.off_fnodes;
+    const bool fast = accel == 1;
     std::memcpy(P.cam, cam, sizeof(float) * 21);
     if (row_step == 0) row_step = 1;
     P.nx = nx; P.ny = ny; P.row_begin = row_begin; P.row_step = row_step;
@@ -50,7 +53,8 @@ extern "C" int harness_render(const rtiow_scene_desc_t* desc, const rtiow_camera
             uint32_t segs;
             for (;;) {
                 float best_t;
-                const uint32_t best = has_frames ? hit_top_stream<true>(sc, st, best_t) : hit_top_stream<false>(sc, st, best_t);
+                const uint32_t best = has_frames ? (fast ? hit_top_stream<true, true>(sc, st, best_t) : hit_top_stream<true, false>(sc, st, best_t))
+                                                 : (fast ? hit_top_stream<false, true>(sc, st, best_t) : hit_top_stream<false, false>(sc, st, best_t));
                 segs = st.bounce + 1u;
                 if (shade_and_scatter(sc, P, st, best, best_t, result)) break;
             }

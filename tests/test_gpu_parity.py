@@ -114,7 +114,7 @@ def test_execution_shape_does_not_change_results():
     multi = R.par_cast(nx, ny, ns, cam, world).rgb
     assert world.stats()["passes"] > 1 and bits_equal(multi, ref)
     world.set_tuning(staging_mib=2048)
-    for threads in (128, 256, 512, 1024):
+    for threads in (256, 512, 768):
         world.set_tuning(cta_threads=threads)
         assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, ref), threads
     world.set_tuning(cta_threads=0, force_global=True)
@@ -124,6 +124,10 @@ def test_execution_shape_does_not_change_results():
     assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, ref)
     world.set_tuning()
     assert world.stats()["accel_subtrees"] > 0
+    assert world.stats()["traversal"] == 0               # re-indexed tree, conservative inner box tests (the default)
+    world.set_traversal(2)                               # the same tree with the reference's Aabb::hit at every node
+    assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, ref)
+    assert world.stats()["traversal"] == 2 and world.stats()["accel_subtrees"] > 0
     world.set_traversal(1)                               # the reference's own visiting order instead of the re-indexed tree
     assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, ref)
     assert world.stats()["accel_subtrees"] == 0

@@ -173,7 +173,7 @@ def test_flattened_stream_logic_matches_golden():
     """The kernel's per-path code, compiled for the host, over the product's flattened scenes."""
     for key, name, nx, ny, ns, bvh, want, segs in golden_cases():
         world, cam = R.build_scene(name, nx, ny, use_bvh=bvh)
-        for accel in (True, False):      # the re-indexed Bvh traversal and the reference-order stream
+        for accel in (1, 2, 0):          # fast re-indexed traversal, exact re-indexed traversal, reference-order stream
             got, smp = H.render(world, cam, nx, ny, ns, want_samples=True, accel=accel)
             assert n_diff(got, want) == 0, (key, accel)
             assert int(smp[..., 3].sum()) == segs, (key, accel)
@@ -181,7 +181,7 @@ def test_flattened_stream_logic_matches_golden():
 
 @pytest.mark.parametrize("name,bvh", [("book1", True), ("cornell", False), ("final", False), ("final", True),
                                       ("kitchen_sink", True), ("kitchen_sink", False), ("volume_test", False)])
-@pytest.mark.parametrize("accel", [True, False])
+@pytest.mark.parametrize("accel", [1, 2, 0])
 def test_flattened_stream_logic_matches_oracle_per_sample(oracle, name, bvh, accel):
     nx, ny, ns = 40, 30, 5
     world, cam = R.build_scene(name, nx, ny, use_bvh=bvh)
@@ -196,7 +196,7 @@ def test_reindexed_subtrees_layout():
     """Which Bvh subtrees the device library re-indexes: pure box/primitive subtrees
     become one ACCEL item + an (n_leaves - 1)-node tree; media, frame switches and list elements stay
     on the reference-order stream."""
-    def layout(name, bvh, accel=True):
+    def layout(name, bvh, accel=2):
         world, cam = R.build_scene(name, 8, 8, use_bvh=bvh)
         lay = np.zeros(4, np.uint32)
         H.render(world, cam, 8, 8, 1, accel=accel, layout=lay)
@@ -204,7 +204,9 @@ def test_reindexed_subtrees_layout():
     c, l = layout("book1", True)
     assert l["accels"] == 1 and l["nodes"] == c["spheres"] - 1            # one leaf per sphere
     assert l["items"] == c["spheres"] + 2 and l["depth"] <= 30            # ACCEL + spheres + END: no BBOX items left
-    c, l = layout("book1", True, accel=False)
+    c, l = layout("book1", True, accel=1)                                 # fast tree: each leaf keeps its own BBOX item
+    assert l["accels"] == 1 and l["items"] == 2 * c["spheres"] + 2
+    c, l = layout("book1", True, accel=0)
     assert l == dict(items=c["items"], nodes=0, accels=0, depth=0)        # the stream as flattened
     c, l = layout("book1", False)
     assert l["accels"] == 0                                               # a plain list has no boxes to re-index
