@@ -33,8 +33,8 @@ struct KParams {
     float cam[21];              // rtiow_camera_t
     uint32_t nx, ny, row_begin, n_rows, row_step;  // rows row_begin, row_begin + row_step, ... (n_rows of them)
     uint32_t s_begin, s_count;  // samples [s_begin, s_begin + s_count) of every pixel in this pass
-    uint32_t npix, n_groups;
-    uint32_t s_chunk, n_chunks, n_units;  // work unit = s_chunk samples of one 32-pixel group
+    uint32_t npix, tiles_x;     // the row block is cut into 8x4-pixel tiles, tiles_x per tile row
+    uint32_t s_chunk, n_chunks, n_units;  // work unit = s_chunk samples of one tile
     uint32_t key0, key1;
     uint32_t bg_kind;
     float bg0[3], bg1[3];

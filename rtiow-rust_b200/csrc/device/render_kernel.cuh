@@ -75,8 +75,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
 
-    // ---- warp-uniform job pool: the samples of one 32-pixel group ----------------------------
-    uint32_t pool_base = 0, pool_valid = 32, pool_next = 0, pool_end = 0, pool_s0 = 0;
+    // ---- warp-uniform job pool: the samples of one 8x4-pixel tile ------------------------------
+    uint32_t pool_x0 = 0, pool_r0 = 0, pool_next = 0, pool_end = 0, pool_s0 = 0;
     bool exhausted = false;
 
     // ---- per-lane path state ------------------------------------------------------------------
@@ -98,10 +98,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
             for (;;) {
                 const uint32_t avail = pool_end - pool_next;
                 if (need && !fresh && my_rank < avail) {
+                    // job = sample-major over the tile: 32 neighbouring pixels of one sample first
                     const uint32_t job = pool_next + my_rank;
-                    st.samp = P.s_begin + pool_s0 + job / pool_valid;
-                    st.pix = pool_base + job % pool_valid;
-                    fresh = true;
+                    const uint32_t x = pool_x0 + (job & 7u), r = pool_r0 + ((job >> 3) & 3u);
+                    if (x < P.nx && r < P.n_rows) {  // tiles on the right / bottom edge are partly outside
+                        st.samp = P.s_begin + pool_s0 + (job >> 5);
+                        st.pix = r * P.nx + x;
+                        fresh = true;
+                    }
                 }
                 const uint32_t taken = remaining < avail ? remaining : avail;
                 pool_next += taken;
@@ -112,14 +116,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
                 if (lane == 0) u = atomicAdd(P.work_counter, 1u);
                 u = __shfl_sync(0xffffffffu, u, 0);
                 if (u >= P.n_units) { exhausted = true; break; }
-                // unit u = samples [c * s_chunk, ...) of pixel group g; small units keep the tail short
+                // unit u = samples [c * s_chunk, ...) of tile g; small units keep the tail short
                 const uint32_t g = u / P.n_chunks, c = u - g * P.n_chunks;
-                pool_base = g * 32u;
-                pool_valid = P.npix - pool_base < 32u ? P.npix - pool_base : 32u;
+                const uint32_t ty = g / P.tiles_x;
+                pool_x0 = (g - ty * P.tiles_x) * 8u;
+                pool_r0 = ty * 4u;
                 pool_s0 = c * P.s_chunk;
                 const uint32_t s_n = P.s_count - pool_s0 < P.s_chunk ? P.s_count - pool_s0 : P.s_chunk;
                 pool_next = 0u;
-                pool_end = pool_valid * s_n;
+                pool_end = 32u * s_n;
             }
         }
         if (fresh) {

@@ -24,7 +24,18 @@ def lib():
         _lib = C.CDLL(_SO)
         _lib.harness_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
                                         C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32]
+        _lib.harness_trace_rays.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
     return _lib
+
+
+def trace_rays(world, rays, accel):
+    """hit_top for explicit rays [n, 7] = (origin, direction, time) -> uint32 [n, 2] = (winner id, bits of t)."""
+    rays = np.ascontiguousarray(rays, np.float32)
+    out = np.zeros((rays.shape[0], 2), np.uint32)
+    rc = lib().harness_trace_rays(C.cast(world.desc, C.c_void_p), rays.shape[0], rays.ctypes.data, out.ctypes.data, int(accel))
+    if rc:
+        raise RuntimeError(f"harness_trace_rays failed: {rc}")
+    return out
 
 
 def render(world, camera, nx, ny, ns, seed=0xDEADBEEF, rows=None, want_samples=False, accel=True, layout=None, row_step=1):

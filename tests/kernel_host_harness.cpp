@@ -71,3 +71,46 @@ extern "C" __attribute__((visibility("default"))) int harness_render(const rtiow
     }
     return 0;
 }
+
+// hit_top for caller-supplied rays: n rays as {ox, oy, oz, dx, dy, dz, time}; out[2*i] = winning item of the
+// REFERENCE-ORDER stream (0xffffffff = none, comparable across traversal modes through its primitive record),
+// out[2*i+1] = bits of t.  Used to pit the three traversals against each other on adversarial rays.
+extern "C" __attribute__((visibility("default"))) int harness_trace_rays(const rtiow_scene_desc_t* desc, uint32_t n, const float* rays,
+                                                                         uint32_t* out, int accel) {
+    using namespace rtiow;
+    bool has_frames = false, uses_perlin = false;
+    std::string msg;
+    if (int rc = validate_desc(desc, &has_frames, &uses_perlin, &msg)) return rc;
+    BlobLayout lay{};
+    const std::vector<unsigned char> blob = build_blob(desc, uses_perlin, &lay, accel == 1 ? kBlobFast : (accel == 2 ? kBlobExact : kBlobReferenceOrder));
+    KParams P{};
+    P.blob = blob.data();
+    P.off_nodes = lay.off_nodes; P.off_frames = lay.off_frames; P.off_ops = lay.off_ops; P.off_mats = lay.off_mats; P.off_tex = lay.off_tex;
+    P.off_pvecs = lay.off_pvecs; P.off_pperm = lay.off_pperm; P.off_fnodes = lay.off_fnodes;
+    const SceneT<MemPtr> sc = scene_views(MemPtr{blob.data()}, P);
+    const bool fast = accel == 1;
+    for (uint32_t i = 0; i < n; ++i) {
+        PathState st;
+        st.pix = 0; st.samp = 0; st.bounce = 0;
+        st.rng = Rng{1u, 2u, i, 0u};
+        st.ro = mk(rays[7 * i], rays[7 * i + 1], rays[7 * i + 2]);
+        st.rd = mk(rays[7 * i + 3], rays[7 * i + 4], rays[7 * i + 5]);
+        st.rtime = rays[7 * i + 6];
+        st.strength = splat(1.f);
+        float best_t = 0.f;
+        const uint32_t best = has_frames ? (fast ? hit_top_stream<true, true>(sc, st, best_t) : hit_top_stream<true, false>(sc, st, best_t))
+                                         : (fast ? hit_top_stream<false, true>(sc, st, best_t) : hit_top_stream<false, false>(sc, st, best_t));
+        // identify the winner by its primitive record (item numbering differs between blobs)
+        uint32_t id = 0xffffffffu;
+        if (best != kNoHit) {
+            const float4 a = sc.item_a(best), b = sc.item_b(best);
+            uint32_t h = 2166136261u;
+            const uint32_t w[8] = {f2u(a.x), f2u(a.y), f2u(a.z), f2u(a.w) & 15u, f2u(b.x), f2u(b.y), f2u(b.z), f2u(b.w)};
+            for (uint32_t k = 0; k < 8; ++k) h = (h ^ w[k]) * 16777619u;
+            id = h & 0x7fffffffu;
+        }
+        out[2 * i] = id;
+        out[2 * i + 1] = best == kNoHit ? 0u : f2u(best_t);
+    }
+    return 0;
+}
