@@ -214,12 +214,13 @@ RTIOW_API int rtiow_b200_render_rows_device(rtiow_scene_t* scene, const rtiow_ca
                                   uint32_t ns, uint64_t seed, uint32_t row_begin, uint32_t row_end,
                                   float* d_out_rows, void* cuda_stream);
 
-/* Rows row_begin, row_begin + row_step, ... below row_end, packed in that order: with
- * row_begin = rank and row_step = n_ranks every GPU gets an equal mix of cheap (sky) and expensive
- * scanlines.  Each row is bit-identical to the same row of rtiow_b200_render. */
+/* Bands of `band_rows` consecutive rows starting at row_begin, row_begin + row_step, ... (clipped to
+ * row_end), packed in that order; 1 <= band_rows <= row_step.  With band_rows = B, row_begin = rank * B
+ * and row_step = n_ranks * B every GPU gets an equal mix of cheap (sky) and expensive scanlines while
+ * its 8x4-pixel work tiles stay compact.  Each row is bit-identical to the same row of rtiow_b200_render. */
 RTIOW_API int rtiow_b200_render_rows_strided_device(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny,
                                           uint32_t ns, uint64_t seed, uint32_t row_begin, uint32_t row_end,
-                                          uint32_t row_step, float* d_out_rows, void* cuda_stream);
+                                          uint32_t row_step, uint32_t band_rows, float* d_out_rows, void* cuda_stream);
 
 /* Parity/debug: per-sample radiance before the fold, HOST memory,
  * (row_end-row_begin)*nx*ns*4 floats laid out [row][x][sample]{r,g,b,segments}. */

@@ -95,7 +95,7 @@ def abi():
         L.rtiow_b200_render.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, vp]
         L.rtiow_b200_render_rows.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, u32, u32, vp]
         L.rtiow_b200_render_rows_device.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, u32, u32, vp, vp]
-        L.rtiow_b200_render_rows_strided_device.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, u32, u32, u32, vp, vp]
+        L.rtiow_b200_render_rows_strided_device.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, u32, u32, u32, u32, vp, vp]
         L.rtiow_b200_render_samples.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, u32, u32, vp]
         L.rtiow_b200_ppm_quantise.argtypes = [vp, vp, C.c_size_t, vp]
         L.rtiow_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]

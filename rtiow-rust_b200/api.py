@@ -189,16 +189,16 @@ def render_samples(nx, ny, ns, camera, world, seed=DEFAULT_SEED, device=0, rows=
     return out
 
 
-def render_rows_device(nx, ny, ns, camera, world, out_tensor, rows, seed=DEFAULT_SEED, stream=None, row_step=1):
-    """Enqueue rows begin, begin + row_step, ... below end (packed) into a CUDA torch tensor (float32)
-    on `stream` (a torch.cuda.Stream, default: current).  Nothing is synchronised."""
+def render_rows_device(nx, ny, ns, camera, world, out_tensor, rows, seed=DEFAULT_SEED, stream=None, row_step=1, row_band=1):
+    """Enqueue bands of row_band rows starting at begin, begin + row_step, ... (clipped to end, packed) into
+    a CUDA torch tensor (float32) on `stream` (a torch.cuda.Stream, default: current).  Nothing is synchronised."""
     import torch
     assert out_tensor.is_cuda and out_tensor.dtype == torch.float32 and out_tensor.is_contiguous()
     r0, r1 = rows
-    assert out_tensor.numel() >= ((r1 - r0 + row_step - 1) // row_step) * nx * 3
+    assert out_tensor.numel() >= sum(min(row_band, r1 - b) for b in range(r0, r1, row_step)) * nx * 3
     dev = out_tensor.device.index or 0
     s = stream if stream is not None else torch.cuda.current_stream(dev)
-    _check(N.abi().rtiow_b200_render_rows_strided_device(world.gpu(dev), C.byref(camera.rec), nx, ny, ns, seed, r0, r1, row_step,
+    _check(N.abi().rtiow_b200_render_rows_strided_device(world.gpu(dev), C.byref(camera.rec), nx, ny, ns, seed, r0, r1, row_step, row_band,
                                                          C.c_void_p(out_tensor.data_ptr()), C.c_void_p(s.cuda_stream)))
 
 

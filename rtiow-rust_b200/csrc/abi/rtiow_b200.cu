@@ -280,11 +280,11 @@ int ensure_uploaded(rtiow_scene* s, rtiow_scene::Blob& B) {
 }
 
 int check_render_args(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny, uint32_t ns, uint32_t r0,
-                      uint32_t r1, const void* out, uint32_t step = 1) {
+                      uint32_t r1, const void* out, uint32_t step = 1, uint32_t band = 1) {
     if (!s || !cam || !out) return set_err(RTIOW_ERR_INVALID_ARG, "null argument");
     if (nx == 0 || ny == 0 || ns == 0) return set_err(RTIOW_ERR_INVALID_ARG, "nx, ny and ns must be non-zero");
     if (r0 >= r1 || r1 > ny) return set_err(RTIOW_ERR_INVALID_ARG, "row range must satisfy row_begin < row_end <= ny");
-    if (step == 0) return set_err(RTIOW_ERR_INVALID_ARG, "row_step must be non-zero");
+    if (step == 0 || band == 0 || band > step) return set_err(RTIOW_ERR_INVALID_ARG, "need 1 <= band_rows <= row_step");
     if (static_cast<uint64_t>(nx) * ny >= (1ull << 32)) return set_err(RTIOW_ERR_INVALID_ARG, "image too large");
     if (!(cam->time0 < cam->time1))  // rand's gen_range asserts low < high (camera.rs:55)
         return set_err(RTIOW_ERR_INVALID_ARG, "Uniform::sample_single called with low >= high (camera exposure)");
@@ -293,9 +293,12 @@ int check_render_args(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, ui
 
 // Enqueue a full render of rows [r0, r1) into device buffer d_out (rgb floats) and/or d_samples.
 int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny, uint32_t ns, uint64_t seed,
-                   uint32_t r0, uint32_t r1, float* d_out, float4* d_samples, cudaStream_t stream, uint32_t step = 1) {
+                   uint32_t r0, uint32_t r1, float* d_out, float4* d_samples, cudaStream_t stream, uint32_t step = 1,
+                   uint32_t band = 1) {
     CK(cudaSetDevice(s->device));
-    const uint32_t n_rows = (r1 - r0 + step - 1) / step;  // rows r0, r0 + step, ... below r1
+    // bands of `band` rows starting at r0, r0 + step, ..., clipped to r1
+    const uint32_t n_full = (r1 - r0) / step, rest = (r1 - r0) - n_full * step;
+    const uint32_t n_rows = n_full * band + std::min(rest, band);
     const uint64_t npix64 = static_cast<uint64_t>(n_rows) * nx;
     const uint32_t npix = static_cast<uint32_t>(npix64);
     const uint64_t budget = static_cast<uint64_t>(s->staging_mib) << 20;
@@ -342,7 +345,7 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     P.off_tex = B.lay.off_tex; P.off_pvecs = B.lay.off_pvecs; P.off_pperm = B.lay.off_pperm;
     P.off_fnodes = B.lay.off_fnodes;
     std::memcpy(P.cam, cam, sizeof(float) * 21);
-    P.nx = nx; P.ny = ny; P.row_begin = r0; P.n_rows = n_rows; P.row_step = step;
+    P.nx = nx; P.ny = ny; P.row_begin = r0; P.n_rows = n_rows; P.row_step = step; P.row_band = band;
     P.npix = npix; P.tiles_x = tiles_x;
     P.key0 = static_cast<uint32_t>(seed); P.key1 = static_cast<uint32_t>(seed >> 32);
     P.bg_kind = s->bg_kind;
@@ -350,7 +353,16 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     P.staging = static_cast<float4*>(W.staging.p);
     P.work_counter = W.d_counter;
 
-    const uint32_t chunk_pref = s->sample_chunk ? s->sample_chunk : 8u;
+    // Work unit = s_chunk samples of one tile.  The kernel ends when the last warp finishes its last unit, so
+    // a unit must be a small fraction of a warp's share: the largest chunk of 8, 4, 2, 1 that still leaves
+    // every resident warp ~48 units (one GPU at C2: 8; an eighth of the frame on each of 8 GPUs: 1).
+    uint32_t chunk_pref = s->sample_chunk;
+    if (chunk_pref == 0) {
+        const uint64_t want_units = 48ull * grid * warps_per_cta;
+        chunk_pref = 8u;
+        while (chunk_pref > 1u && static_cast<uint64_t>(n_groups) * ((std::min(s_pass, ns) + chunk_pref - 1) / chunk_pref) < want_units)
+            chunk_pref >>= 1;
+    }
     if (int rc = ensure_events(s, 1 + 2 * n_pass)) return rc;
     s->events_used = 0;
     CK(cudaMemsetAsync(W.d_segs, 0, sizeof(unsigned long long), stream));
@@ -524,10 +536,10 @@ int rtiow_b200_render_rows_device(rtiow_scene_t* s, const rtiow_camera_t* cam, u
 }
 
 int rtiow_b200_render_rows_strided_device(rtiow_scene_t* s, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny, uint32_t ns,
-                                          uint64_t seed, uint32_t r0, uint32_t r1, uint32_t step, float* d_out,
+                                          uint64_t seed, uint32_t r0, uint32_t r1, uint32_t step, uint32_t band, float* d_out,
                                           void* cuda_stream) {
-    if (int rc = check_render_args(s, cam, nx, ny, ns, r0, r1, d_out, step)) return rc;
-    return enqueue_render(s, cam, nx, ny, ns, seed, r0, r1, d_out, nullptr, static_cast<cudaStream_t>(cuda_stream), step);
+    if (int rc = check_render_args(s, cam, nx, ny, ns, r0, r1, d_out, step, band)) return rc;
+    return enqueue_render(s, cam, nx, ny, ns, seed, r0, r1, d_out, nullptr, static_cast<cudaStream_t>(cuda_stream), step, band);
 }
 
 int rtiow_b200_render_rows(rtiow_scene_t* s, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny, uint32_t ns, uint64_t seed,

@@ -31,7 +31,8 @@ struct KParams {
     uint32_t off_nodes, off_frames, off_ops, off_mats, off_tex, off_pvecs, off_pperm;
     uint32_t off_fnodes;        // conservative-test nodes (accel_build.hpp FastNode); 0 = none
     float cam[21];              // rtiow_camera_t
-    uint32_t nx, ny, row_begin, n_rows, row_step;  // rows row_begin, row_begin + row_step, ... (n_rows of them)
+    // packed row r is image row row_begin + (r / row_band) * row_step + r % row_band (n_rows of them)
+    uint32_t nx, ny, row_begin, n_rows, row_step, row_band;
     uint32_t s_begin, s_count;  // samples [s_begin, s_begin + s_count) of every pixel in this pass
     uint32_t npix, tiles_x;     // the row block is cut into 8x4-pixel tiles, tiles_x per tile row
     uint32_t s_chunk, n_chunks, n_units;  // work unit = s_chunk samples of one tile
@@ -311,7 +312,8 @@ RT_HD V3 in_unit_sphere(const Rng& rng, uint32_t bounce) {  // vec3.rs:19-26
 // ------------------------------------------------------------------------------------------------
 RT_HD void generate_camera_ray(const KParams& P, PathState& st) {
     const uint32_t r = st.pix / P.nx, x = st.pix - r * P.nx;
-    const uint32_t y = P.ny - 1u - (P.row_begin + r * P.row_step);  // (0..ny).rev()  lib.rs:326-330
+    const uint32_t band = r / P.row_band;
+    const uint32_t y = P.ny - 1u - (P.row_begin + band * P.row_step + (r - band * P.row_band));  // (0..ny).rev()  lib.rs:326-330
     st.rng.pixel = y * P.nx + x;
     st.rng.sample = st.samp;
     const U4 cw = st.rng.block(0u, PURPOSE_CAMERA, 0u);

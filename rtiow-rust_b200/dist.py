@@ -4,10 +4,11 @@ so the assembled image is bit-identical for every world size.
 
 Two partitions of the rows:
 
-  interleaved (default)  rank r renders rows r, r + G, r + 2G, ...  Every GPU gets the same mix of cheap
-                         (sky: one segment) and expensive (ground, spheres) scanlines.  The ranks' packed
-                         row blocks are exchanged with ONE NCCL all-gather and de-interleaved by a single
-                         strided device copy.
+  interleaved (default)  the frame is cut into bands of 4 scanlines (the height of the kernel's 8x4-pixel
+                         work tiles) and rank r renders bands r, r + G, r + 2G, ...  Every GPU gets the same
+                         mix of cheap (sky: one segment) and expensive (ground, spheres) scanlines.  The
+                         ranks' packed row blocks are exchanged with ONE NCCL all-gather and de-interleaved
+                         by a single strided device copy.
   contiguous             rank r renders rows [r*ny/G, (r+1)*ny/G) straight into its slice of the frame and
                          the all-gather is in place (BASELINE.json's "scanline block" wording); simpler, but
                          on the book-1 scene the top ranks finish early.
@@ -22,36 +23,48 @@ from . import _native as N
 from . import api
 
 
+BAND_ROWS = 4  # height of the megakernel's work tiles (render_kernel.cuh)
+
+
 class RowShard:
     """Which output rows (row 0 = top) rank `rank` of `world_size` renders."""
 
-    def __init__(self, ny, rank=0, world_size=1, interleaved=True):
+    def __init__(self, ny, rank=0, world_size=1, interleaved=True, band=None):
         self.ny, self.rank, self.world_size, self.interleaved = ny, rank, world_size, bool(interleaved)
         if self.interleaved:
-            self.counts = [(ny - r + world_size - 1) // world_size if r < ny else 0 for r in range(world_size)]
-            self.begin, self.end, self.step = min(rank, ny), ny, world_size
+            # bands of `band` rows dealt round-robin; single rows when the frame is too small for that to balance
+            self.band = band if band is not None else (BAND_ROWS if ny >= 8 * BAND_ROWS * world_size else 1)
+            n_bands = (ny + self.band - 1) // self.band
+            self.counts = [len(self._band_rows(r, n_bands)) for r in range(world_size)]
+            self.begin, self.end, self.step = min(rank * self.band, ny), ny, world_size * self.band
+            bands_per_rank = (n_bands + world_size - 1) // world_size
+            self.max_rows = bands_per_rank * self.band          # every rank's block is whole band slots
         else:
+            self.band = 1
             base, extra = divmod(ny, world_size)
             self.counts = [base + (1 if r < extra else 0) for r in range(world_size)]
             self.begins = [sum(self.counts[:r]) for r in range(world_size)]
             self.begin = self.begins[rank]
             self.end = self.begin + self.counts[rank]
             self.step = 1
+            self.max_rows = max(self.counts)
         self.n_rows = self.counts[rank]
-        self.max_rows = max(self.counts)
-        self.uniform = len(set(self.counts)) == 1
+        self.uniform = len(set(self.counts)) == 1 and self.max_rows == self.counts[0]
+
+    def _band_rows(self, r, n_bands):
+        return [row for b in range(r, n_bands, self.world_size) for row in range(b * self.band, min((b + 1) * self.band, self.ny))]
 
     def rows(self, rank=None):
         """Global row indices of a rank, in the order they are packed."""
         r = self.rank if rank is None else rank
         if self.interleaved:
-            return list(range(r, self.ny, self.world_size))
+            return self._band_rows(r, (self.ny + self.band - 1) // self.band)
         b = sum(self.counts[:r])
         return list(range(b, b + self.counts[r]))
 
     def describe(self):
-        kind = "interleaved rows (rank r: r, r+G, ...)" if self.interleaved else "contiguous blocks"
-        return f"{self.max_rows} rows x {self.world_size} rank(s), {kind}"
+        kind = (f"interleaved bands of {self.band} row(s) (rank r: bands r, r+G, ...)" if self.interleaved else "contiguous blocks")
+        return f"{max(self.counts)} rows x {self.world_size} rank(s), {kind}"
 
 
 def assemble(parts, shard, xp=np):
@@ -59,11 +72,11 @@ def assemble(parts, shard, xp=np):
     torch tensors (one strided copy)."""
     G, mx = shard.world_size, shard.max_rows
     if shard.interleaved:
-        # row lr of rank r is global row lr * G + r
-        nx = parts.shape[2]
+        # band slot k of rank r is global band k * G + r: [G, slots, B, nx, 3] -> [slots, G, B, nx, 3]
+        nx, B = parts.shape[2], shard.band
         if xp is np:
-            return np.ascontiguousarray(parts.transpose(1, 0, 2, 3).reshape(mx * G, nx, 3)[:shard.ny])
-        return parts.permute(1, 0, 2, 3).reshape(mx * G, nx, 3)[:shard.ny].contiguous()
+            return np.ascontiguousarray(parts.reshape(G, mx // B, B, nx, 3).transpose(1, 0, 2, 3, 4).reshape(mx * G, nx, 3)[:shard.ny])
+        return parts.reshape(G, mx // B, B, nx, 3).permute(1, 0, 2, 3, 4).reshape(mx * G, nx, 3)[:shard.ny].contiguous()
     pieces = [parts[r, :c] for r, c in enumerate(shard.counts)]
     if xp is np:
         return np.concatenate(pieces)
@@ -96,7 +109,7 @@ def render_sharded_device(nx, ny, ns, camera, world, bufs, seed=api.DEFAULT_SEED
     import torch.distributed as dist
     sh = bufs.shard
     if sh.n_rows > 0:
-        api.render_rows_device(nx, ny, ns, camera, world, bufs.mine, (sh.begin, sh.end), seed=seed, row_step=sh.step)
+        api.render_rows_device(nx, ny, ns, camera, world, bufs.mine, (sh.begin, sh.end), seed=seed, row_step=sh.step, row_band=sh.band)
     if sh.world_size > 1:
         if bufs.parts is not None:
             dist.all_gather_into_tensor(bufs.parts.view(sh.world_size * sh.max_rows, nx, 3), bufs.mine)

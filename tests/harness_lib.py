@@ -23,7 +23,7 @@ def lib():
                                    "-shared", "-o", _SO, src])
         _lib = C.CDLL(_SO)
         _lib.harness_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
-                                        C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32]
+                                        C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32]
         _lib.harness_trace_rays.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
     return _lib
 
@@ -38,15 +38,16 @@ def trace_rays(world, rays, accel):
     return out
 
 
-def render(world, camera, nx, ny, ns, seed=0xDEADBEEF, rows=None, want_samples=False, accel=True, layout=None, row_step=1):
-    """rows=(begin, end): rows begin, begin + row_step, ... below end."""
+def render(world, camera, nx, ny, ns, seed=0xDEADBEEF, rows=None, want_samples=False, accel=True, layout=None, row_step=1,
+           row_band=1):
+    """rows=(begin, end): bands of row_band rows starting at begin, begin + row_step, ... clipped to end."""
     r0, r1 = rows if rows is not None else (0, ny)
-    n_rows = (r1 - r0 + row_step - 1) // row_step
+    n_rows = sum(min(row_band, r1 - b) for b in range(r0, r1, row_step))
     img = np.zeros((n_rows, nx, 3), np.float32)
     smp = np.zeros((n_rows, nx, ns, 4), np.float32) if want_samples else None
     rc = lib().harness_render(C.cast(world.desc, C.c_void_p), C.byref(camera.rec), nx, ny, ns, seed, r0, r1,
                               img.ctypes.data, smp.ctypes.data if want_samples else None, int(accel),
-                              layout.ctypes.data if layout is not None else None, row_step)
+                              layout.ctypes.data if layout is not None else None, row_step, row_band)
     if rc:
         raise RuntimeError(f"harness_render failed: {rc}")
     return img, smp

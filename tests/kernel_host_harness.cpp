@@ -17,7 +17,7 @@
 // reference-order stream.
 extern "C" __attribute__((visibility("default"))) int harness_render(const rtiow_scene_desc_t* desc, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny,
                               uint32_t ns, uint64_t seed, uint32_t row_begin, uint32_t row_end, float* out_rgb,
-                              float* out_samples, int accel, uint32_t* layout_out, uint32_t row_step) {
+                              float* out_samples, int accel, uint32_t* layout_out, uint32_t row_step, uint32_t row_band) {
     using namespace rtiow;
     bool has_frames = false, uses_perlin = false;
     std::string msg;
@@ -33,8 +33,10 @@ extern "C" __attribute__((visibility("default"))) int harness_render(const rtiow
     const bool fast = accel == 1;
     std::memcpy(P.cam, cam, sizeof(float) * 21);
     if (row_step == 0) row_step = 1;
-    P.nx = nx; P.ny = ny; P.row_begin = row_begin; P.row_step = row_step;
-    P.n_rows = (row_end - row_begin + row_step - 1) / row_step;  // rows row_begin, +step, ... below row_end
+    if (row_band == 0) row_band = 1;
+    P.nx = nx; P.ny = ny; P.row_begin = row_begin; P.row_step = row_step; P.row_band = row_band;
+    P.n_rows = 0;  // bands of row_band rows starting at row_begin, +step, ... clipped to row_end
+    for (uint32_t b = row_begin; b < row_end; b += row_step) P.n_rows += row_end - b < row_band ? row_end - b : row_band;
     P.s_begin = 0; P.s_count = ns;
     P.npix = P.n_rows * nx;
     P.key0 = static_cast<uint32_t>(seed); P.key1 = static_cast<uint32_t>(seed >> 32);

@@ -35,7 +35,7 @@ def _worker(rank, world_size, port, ny, interleaved, out_dir):
     nx, ns = 40, 3
     world, cam = R.build_scene("kitchen_sink", nx, ny, use_bvh=True)
     shard = rdist.RowShard(ny, rank, world_size, interleaved)
-    local, _ = H.render(world, cam, nx, ny, ns, rows=(shard.begin, shard.end), row_step=shard.step)
+    local, _ = H.render(world, cam, nx, ny, ns, rows=(shard.begin, shard.end), row_step=shard.step, row_band=shard.band)
     assert local.shape[0] == shard.n_rows
     full = rdist.gather_rows_cpu(local, shard, nx)
     np.save(os.path.join(out_dir, f"rank{rank}.npy"), full)
@@ -44,7 +44,7 @@ def _worker(rank, world_size, port, ny, interleaved, out_dir):
 
 
 @pytest.mark.parametrize("interleaved", [True, False])
-@pytest.mark.parametrize("ny", [30, 31])   # 31: uneven split (16 + 15 rows)
+@pytest.mark.parametrize("ny", [30, 31, 70])   # 31: uneven split (16 + 15 rows); 70: bands of 4 rows, the last one partial
 def test_two_rank_row_sharding_is_bit_identical(tmp_path, ny, interleaved):
     sys.path.insert(0, HERE)
     import harness_lib as H
@@ -60,13 +60,16 @@ def test_two_rank_row_sharding_is_bit_identical(tmp_path, ny, interleaved):
 
 def test_row_shard_partition():
     from rtiow_rust_b200.dist import RowShard, assemble
-    for ny, ws in ((800, 8), (800, 3), (5, 8), (1, 2), (3200, 8)):
+    for ny, ws in ((800, 8), (800, 3), (5, 8), (1, 2), (3200, 8), (70, 2), (803, 8)):
         for inter in (True, False):
             shards = [RowShard(ny, r, ws, inter) for r in range(ws)]
             rows = sorted(sum((s.rows() for s in shards), []))
             assert rows == list(range(ny)), (ny, ws, inter)                       # every row exactly once
             assert all(len(s.rows()) == s.n_rows for s in shards)
-            assert max(s.n_rows for s in shards) - min(s.n_rows for s in shards) <= 1
+            assert max(s.n_rows for s in shards) - min(s.n_rows for s in shards) <= shards[0].band
+            for s in shards:                                                      # what the kernel is asked for
+                want = [row for b in range(s.begin, s.end, s.step) for row in range(b, min(b + s.band, s.end))]
+                assert want == s.rows()
             # assemble() puts packed row lr of rank r back at its global row
             parts = np.full((ws, shards[0].max_rows, 2, 3), -1, np.float32)
             for s in shards:
@@ -76,4 +79,4 @@ def test_row_shard_partition():
             assert frame.shape == (ny, 2, 3) and np.array_equal(frame[:, 0, 0], np.arange(ny, dtype=np.float32))
     # interleaving balances the book-1 frame: each rank's rows span the whole image
     s = RowShard(800, 3, 8)
-    assert s.rows()[0] == 3 and s.rows()[-1] == 795 and s.step == 8
+    assert s.band == 4 and s.rows()[:5] == [12, 13, 14, 15, 44] and s.rows()[-1] == 783 and s.step == 32 and s.n_rows == 100

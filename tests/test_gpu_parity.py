@@ -89,12 +89,12 @@ def test_strided_rows_and_workspace_reuse():
     nx, ny, ns = 70, 45, 5
     world, cam = R.build_scene("kitchen_sink", nx, ny, use_bvh=True)
     full = R.par_cast(nx, ny, ns, cam, world).rgb
-    for begin, step in ((0, 2), (1, 2), (3, 8), (44, 8), (0, 1)):
-        n = (ny - begin + step - 1) // step
-        out = torch.empty((n, nx, 3), dtype=torch.float32, device="cuda:0")
-        api.render_rows_device(nx, ny, ns, cam, world, out, (begin, ny), row_step=step)
+    for begin, step, band in ((0, 2, 1), (1, 2, 1), (3, 8, 1), (44, 8, 1), (0, 1, 1), (0, 8, 4), (4, 8, 4), (12, 16, 4), (3, 6, 5)):
+        rows = [r for b in range(begin, ny, step) for r in range(b, min(b + band, ny))]   # bands, the last one clipped
+        out = torch.empty((len(rows), nx, 3), dtype=torch.float32, device="cuda:0")
+        api.render_rows_device(nx, ny, ns, cam, world, out, (begin, ny), row_step=step, row_band=band)
         torch.cuda.synchronize()
-        assert bits_equal(out.cpu().numpy(), full[begin::step]), (begin, step)
+        assert bits_equal(out.cpu().numpy(), full[rows]), (begin, step, band)
     for _ in range(3):
         world.upload_fresh(0)
         assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, full)
