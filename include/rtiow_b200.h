@@ -233,7 +233,7 @@ RTIOW_API int rtiow_b200_ppm_quantise(rtiow_scene_t* scene, const float* linear,
 /* Synchronises the scene's device and reports the last render. */
 RTIOW_API int rtiow_b200_get_stats(rtiow_scene_t* scene, rtiow_stats_t* out);
 
-/* Tuning knobs (0 = default / automatic): threads per CTA (128..1024), CTAs per SM, staging budget in MiB,
+/* Tuning knobs (0 = default / automatic): threads per CTA (256, 512 or 768), CTAs per SM, staging budget in MiB,
  * force_global != 0 keeps the scene in global memory even if it fits shared memory. */
 RTIOW_API int rtiow_b200_set_tuning(rtiow_scene_t* scene, uint32_t cta_threads, uint32_t ctas_per_sm, uint32_t staging_mib,
                           int force_global);

@@ -310,6 +310,18 @@ RT_HD V3 in_unit_sphere(const Rng& rng, uint32_t bounce) {  // vec3.rs:19-26
 // lib.rs:366-370 + Camera::get_ray (camera.rs:52-63) for sample st.samp of pixel st.pix
 // (pix counts row-major from the top-left of the rendered row block).
 // ------------------------------------------------------------------------------------------------
+// The third and later draws of gen_range for the shutter time (camera.rs:55): words of the CAMERA
+// blocks 1, 2, ... in order.  Out of line: a draw is rejected only when rounding lands on exposure.end.
+static RT_HD_NOINLINE float shutter_time_retry(Rng rng, float scale, float toff, float t_end) {
+    for (uint32_t k = 0;; ++k) {
+        const U4 tw = rng.block(0u, PURPOSE_CAMERA, 1u + (k >> 2));
+        const uint32_t sel = k & 3u;
+        const uint32_t word = sel == 0 ? tw.x : (sel == 1 ? tw.y : (sel == 2 ? tw.z : tw.w));
+        const float time = f32_1_2(word) * scale + toff;
+        if (time < t_end) return time;
+    }
+}
+
 RT_HD void generate_camera_ray(const KParams& P, PathState& st) {
     const uint32_t r = st.pix / P.nx, x = st.pix - r * P.nx;
     const uint32_t band = r / P.row_band;
@@ -320,10 +332,11 @@ RT_HD void generate_camera_ray(const KParams& P, PathState& st) {
     const float s = (static_cast<float>(x) + unit_f32(cw.x)) / static_cast<float>(P.nx);  // lib.rs:368
     const float t = (static_cast<float>(y) + unit_f32(cw.y)) / static_cast<float>(P.ny);  // lib.rs:369
     V3 disc;
-    for (uint32_t k = 0;; ++k) {  // Vec3::in_unit_disc  vec3.rs:32-39
-        const U4 lw = st.rng.block(0u, PURPOSE_LENS, k >> 1);
-        const uint32_t wa = (k & 1u) ? lw.z : lw.x, wb = (k & 1u) ? lw.w : lw.y;
-        disc = 2.f * mk(unit_f32(wa), unit_f32(wb), 0.f) - mk(1.f, 1.f, 0.f);
+    for (uint32_t j = 0;; ++j) {  // Vec3::in_unit_disc  vec3.rs:32-39; one Philox block serves two attempts
+        const U4 lw = st.rng.block(0u, PURPOSE_LENS, j);
+        disc = 2.f * mk(unit_f32(lw.x), unit_f32(lw.y), 0.f) - mk(1.f, 1.f, 0.f);
+        if (dot(disc, disc) < 1.f) break;
+        disc = 2.f * mk(unit_f32(lw.z), unit_f32(lw.w), 0.f) - mk(1.f, 1.f, 0.f);
         if (dot(disc, disc) < 1.f) break;
     }
     const V3 lens = P.cam[18] * disc;
@@ -331,18 +344,10 @@ RT_HD void generate_camera_ray(const KParams& P, PathState& st) {
     const V3 offset = lens.x * cu + lens.y * cv;
     // rng.gen_range(exposure.start, exposure.end): rand 0.6.5 UniformFloat::sample_single
     const float scale = P.cam[20] - P.cam[19], toff = P.cam[19] - scale;
-    float time;
-    for (uint32_t k = 0;; ++k) {
-        uint32_t word;
-        if (k == 0) word = cw.z;
-        else if (k == 1) word = cw.w;
-        else {
-            const U4 tw = st.rng.block(0u, PURPOSE_CAMERA, 1u + ((k - 2u) >> 2));
-            const uint32_t sel = (k - 2u) & 3u;
-            word = sel == 0 ? tw.x : (sel == 1 ? tw.y : (sel == 2 ? tw.z : tw.w));
-        }
-        time = f32_1_2(word) * scale + toff;
-        if (time < P.cam[20]) break;
+    float time = f32_1_2(cw.z) * scale + toff;
+    if (!(time < P.cam[20])) {
+        time = f32_1_2(cw.w) * scale + toff;
+        if (!(time < P.cam[20])) time = shutter_time_retry(st.rng, scale, toff, P.cam[20]);  // a rounding accident, twice in a row
     }
     const V3 corigin = mk(P.cam[0], P.cam[1], P.cam[2]);
     const V3 llc = mk(P.cam[3], P.cam[4], P.cam[5]);
@@ -574,10 +579,22 @@ RT_HD void trav_leaf_step_fast(const SceneT<Mem>& sc, const Path& path, Trav& tr
     trav_pop(tr, stk);
 }
 
+// Out-of-line copy of prim_hit_t for rare callers (ConstantMedium boundaries).
+struct TimeOnlyView;
+template <class Mem>
+RT_HD_NOINLINE bool prim_hit_outline(const SceneT<Mem> sc, float4 ia, float4 ib, V3 o, V3 d, float time, uint32_t cur_frame,
+                                     uint32_t cur_nops, float t_lo, float t_hi, float& t_out);
+
 struct TimeOnlyView {
     float time;
     RT_HD float rtime() const { return time; }
 };
+
+template <class Mem>
+RT_HD_NOINLINE bool prim_hit_outline(const SceneT<Mem> sc, float4 ia, float4 ib, V3 o, V3 d, float time, uint32_t cur_frame,
+                                     uint32_t cur_nops, float t_lo, float t_hi, float& t_out) {
+    return prim_hit_t(sc, ia, ib, o, d, TimeOnlyView{time}, cur_frame, cur_nops, t_lo, t_hi, t_out);
+}
 
 // ConstantMedium::hit (object.rs:543-575); item i is the medium, item i+1 its boundary primitive.
 struct BestHit {
@@ -600,9 +617,8 @@ RT_HD_NOINLINE BestHit medium_hit(const SceneT<Mem> sc, Rng rng, uint32_t bounce
     }
     const float4 ba = sc.item_a(i + 1u), bb = sc.item_b(i + 1u);
     float t1, t2;
-    const TimeOnlyView tv{time};
-    if (prim_hit_t(sc, ba, bb, mo, md, tv, mframe, m_nops, kF32Min, kF32Max, t1) &&
-        prim_hit_t(sc, ba, bb, mo, md, tv, mframe, m_nops, t1 + 0.0001f, kF32Max, t2)) {
+    if (prim_hit_outline(sc, ba, bb, mo, md, time, mframe, m_nops, kF32Min, kF32Max, t1) &&
+        prim_hit_outline(sc, ba, bb, mo, md, time, mframe, m_nops, t1 + 0.0001f, kF32Max, t2)) {
         t1 = rt_max(t1, kNear);
         t2 = rt_min(t2, best_t);
         if (!(t1 >= t2)) {
@@ -776,14 +792,28 @@ RT_HD bool shade_and_scatter(const SceneT<Mem>& sc, const KParams& P, PathState&
         // accum = accum + strength * (brightness * emission(p)); no scatter -> return accum  (lib.rs:76,88-91)
         result = splat(0.f) + st.strength * (m0.z * material_texture(sc, m0, m1, p));
         return true;
-    } else if (mkind == MAT_LAMBERTIAN) {      // material.rs:57-65
-        const V3 target = p + n + in_unit_sphere(st.rng, st.bounce);
+    }
+    // The scatter draws of this bounce: Vec3::in_unit_sphere (vec3.rs:19-26) for Lambertian, Metal and
+    // Isotropic — attempt k reads words x, y, z of SCATTER block k — and word x of block 0 for the
+    // Dielectric's reflect-or-refract draw.  One loop, so the Philox rounds exist once in the kernel.
+    const bool wants_sphere = mkind != MAT_DIELECTRIC;
+    V3 ius = splat(0.f);
+    float draw0;
+    for (uint32_t k = 0;; ++k) {
+        const U4 w = st.rng.block(st.bounce, PURPOSE_SCATTER, k);
+        draw0 = unit_f32(w.x);
+        if (!wants_sphere) break;
+        ius = 2.f * mk(draw0, unit_f32(w.y), unit_f32(w.z)) - splat(1.f);
+        if (dot(ius, ius) < 1.f) break;
+    }
+    if (mkind == MAT_LAMBERTIAN) {             // material.rs:57-65
+        const V3 target = p + n + ius;
         st.rd = target - p;
         st.ro = p;
         st.strength = st.strength * material_texture(sc, m0, m1, p);
     } else if (mkind == MAT_METAL) {           // material.rs:66-81
         const V3 refl = reflect(into_unit(rd), n);
-        st.rd = refl + m0.z * in_unit_sphere(st.rng, st.bounce);
+        st.rd = refl + m0.z * ius;
         st.ro = p;
         if (dot(st.rd, n) > 0.f) st.strength = st.strength * mk(m1.x, m1.y, m1.z);
         else done = true;                      // absorbed: return accum (= 0)
@@ -803,16 +833,14 @@ RT_HD bool shade_and_scatter(const SceneT<Mem>& sc, const KParams& P, PathState&
         }
         V3 direction;
         bool refracted = refract(rd, outward_normal, ni_over_nt, direction);
-        if (refracted) {  // the draw happens only when refract() is Some (material.rs:96-97)
-            const U4 w = st.rng.block(st.bounce, PURPOSE_SCATTER, 0u);
-            if (!(unit_f32(w.x) >= schlick(cosine, ref_idx))) refracted = false;
-        }
+        // the draw is consumed only when refract() is Some (material.rs:96-97)
+        if (refracted && !(draw0 >= schlick(cosine, ref_idx))) refracted = false;
         if (!refracted) direction = reflect(rd, n);
         st.rd = direction;
         st.ro = p;
         st.strength = st.strength * splat(1.f);
     } else {                                   // Isotropic  material.rs:109-116
-        st.rd = in_unit_sphere(st.rng, st.bounce);
+        st.rd = ius;
         st.ro = p;
         st.strength = st.strength * material_texture(sc, m0, m1, p);
     }
