@@ -320,8 +320,8 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     if (int rc = ensure_uploaded(s, B)) return rc;
     const bool fast = mode == rtiow::kBlobFast && B.lay.n_nodes != 0;
     const bool smem = B.bytes <= smem_cap && !s->force_global;
-    // 0 = automatic: 768 threads (80 registers) per CTA, one CTA per SM; scenes with wrapper frames keep 512
-    const uint32_t threads = s->cta_threads ? s->cta_threads : (s->has_frames ? 512u : 768u);
+    // 0 = automatic: 768 threads (80 registers) per CTA, one CTA per SM
+    const uint32_t threads = s->cta_threads ? s->cta_threads : 768u;
     const KernelVariant var = smem ? rtiow::pick_plain_smem(s->has_frames, fast, threads) : rtiow::pick_plain_global(s->has_frames, fast, threads);
     if (!var.fn) return set_err(RTIOW_ERR_INVALID_ARG, "no kernel instantiation for this cta_threads");
     const size_t dyn_smem = smem ? B.bytes : 0;

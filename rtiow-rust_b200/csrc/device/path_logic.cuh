@@ -202,16 +202,28 @@ RT_HD bool sphere_hit_t(V3 o, V3 d, float radius, float t_lo, float t_hi, float&
 
 RT_HD float axis_of(V3 v, uint32_t axis) { return axis == 0 ? v.x : (axis == 1 ? v.y : v.z); }
 
-// Rect<A>::hit (object.rs:183-218); a = {k, r0.start, r0.end}, b = {r1.start, r1.end}
-RT_HD bool rect_hit_t(V3 o, V3 d, uint32_t axis, float4 ia, float4 ib, float t_lo, float t_hi, float& t_out) {
-    const uint32_t o1 = axis == 0 ? 1u : 0u, o2 = axis == 2 ? 1u : 2u;  // object.rs:153-181
-    const float t = (ia.x - axis_of(o, axis)) / axis_of(d, axis);
+// Rect<A>::hit (object.rs:183-218) with the axis resolved: oa/da = the ray along the rect's axis, (o1, d1) and
+// (o2, d2) along the other two (alphabetical, object.rs:153-181); a = {k, r0.start, r0.end}, b = {r1.start, r1.end}
+RT_HD bool rect_hit_axis(float oa, float da, float o1, float d1, float o2, float d2, float4 ia, float4 ib, float t_lo, float t_hi,
+                         float& t_out) {
+    const float num = ia.x - oa;
+    // A ray leaving a rect starts (after rounding) exactly on its plane more often than not: 0 / d = +-0 < t_lo.
+    // Same verdict as the division below, without its slow path; d = 0 or NaN must divide (0/0 = NaN is a "hit"
+    // in the reference, object.rs:194-197), and so must callers with t_lo <= 0 (ConstantMedium boundaries).
+    if (num == 0.f && t_lo > 0.f && da != 0.f && da == da) return false;
+    const float t = num / da;
     if (t < t_lo || t >= t_hi) return false;
-    const float x = axis_of(o, o1) + t * axis_of(d, o1);
-    const float y = axis_of(o, o2) + t * axis_of(d, o2);
+    const float x = o1 + t * d1;
+    const float y = o2 + t * d2;
     if (x < ia.y || x >= ia.z || y < ib.x || y >= ib.y) return false;
     t_out = t;
     return true;
+}
+RT_HD bool rect_hit_t(V3 o, V3 d, uint32_t axis, float4 ia, float4 ib, float t_lo, float t_hi, float& t_out) {
+    // lanes of a warp walk the same item list, so `axis` is uniform in practice: a branch, not selects
+    if (axis == 0u) return rect_hit_axis(o.x, d.x, o.y, d.y, o.z, d.z, ia, ib, t_lo, t_hi, t_out);
+    if (axis == 1u) return rect_hit_axis(o.y, d.y, o.x, d.x, o.z, d.z, ia, ib, t_lo, t_hi, t_out);
+    return rect_hit_axis(o.z, d.z, o.x, d.x, o.y, d.y, ia, ib, t_lo, t_hi, t_out);
 }
 
 // Any primitive item against a ray (o, d) that is already in frame `cur_frame` (whose chain has
