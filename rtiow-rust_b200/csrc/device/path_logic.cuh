@@ -192,15 +192,22 @@ RT_HD bool sphere_hit_t(V3 o, V3 d, float radius, float t_lo, float t_hi, float&
     const float disc = b * b - a * c;
     if (disc > 0.f) {
         const float sq = sqrtf(disc);
-        float t = (-b - sq) / a;
-        if (t < t_hi && t >= t_lo) { t_out = t; return true; }
-        t = (-b + sq) / a;
-        if (t < t_hi && t >= t_lo) { t_out = t; return true; }
+        // A ray leaving this sphere has c ~ 0, so sqrt(disc) rounds to |b| and one numerator is exactly 0:
+        // 0 / a = 0 < t_lo is the verdict of the division as well, which would take its slow path for it.
+        const bool zero_is_miss = t_lo > 0.f && a > 0.f;
+        float num = -b - sq;
+        if (!(num == 0.f && zero_is_miss)) {
+            const float t = num / a;
+            if (t < t_hi && t >= t_lo) { t_out = t; return true; }
+        }
+        num = -b + sq;
+        if (!(num == 0.f && zero_is_miss)) {
+            const float t = num / a;
+            if (t < t_hi && t >= t_lo) { t_out = t; return true; }
+        }
     }
     return false;
 }
-
-RT_HD float axis_of(V3 v, uint32_t axis) { return axis == 0 ? v.x : (axis == 1 ? v.y : v.z); }
 
 // Rect<A>::hit (object.rs:183-218) with the axis resolved: oa/da = the ray along the rect's axis, (o1, d1) and
 // (o2, d2) along the other two (alphabetical, object.rs:153-181); a = {k, r0.start, r0.end}, b = {r1.start, r1.end}
