@@ -239,6 +239,8 @@ struct rtiow_scene {
     // tuning
     uint32_t cta_threads = 0, ctas_per_sm = 0, staging_mib = 2048, sample_chunk = 0;
     bool force_global = false;
+    uint32_t refill_lanes = 0;     // 0 = automatic
+    bool costly_segments = false;  // the scene has wrapper frames on subtrees or constant media
 
     // last render
     rtiow_stats_t stats{};
@@ -352,6 +354,11 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     std::memcpy(P.bg0, s->bg0, 12); std::memcpy(P.bg1, s->bg1, 12);
     P.staging = static_cast<float4*>(W.staging.p);
     P.work_counter = W.d_counter;
+    // Idle lanes get new pixel-samples once `refill_thr` lanes of the warp wait: generating camera rays costs the
+    // warp the same for 3 lanes as for 30, and rays started together stay coherent.  Waiting costs idle lane
+    // iterations, which are expensive in scenes with media / wrapper frames and frequent where paths are short.
+    // Measured (profiles/r01/sweep_v9_refill_threshold.log): book-1 best at 12, Cornell at 4, final at 1.
+    P.refill_thr = s->refill_lanes ? s->refill_lanes : (s->costly_segments ? 1u : (s->bg_kind == RTIOW_BG_SKY_GRADIENT ? 12u : 4u));
 
     // Work unit = s_chunk samples of one tile.  The kernel ends when the last warp finishes its last unit, so
     // a unit must be a small fraction of a warp's share: the largest chunk of 8, 4, 2, 1 that still leaves
@@ -458,6 +465,8 @@ int rtiow_b200_scene_create(const rtiow_scene_desc_t* d, int device, rtiow_scene
     s->sm_count = info.sm_count;
     s->max_smem_optin = info.max_smem_optin;
     s->has_frames = has_frames;
+    s->costly_segments = has_frames;
+    for (uint32_t i = 0; i < d->n_items; ++i) s->costly_segments |= (d->items[i].a_w & 15u) == RTIOW_ITEM_MEDIUM;
     s->bg_kind = d->background_kind;
     std::memcpy(s->bg0, d->background_c0, 12);
     std::memcpy(s->bg1, d->background_c1, 12);
@@ -476,6 +485,7 @@ int rtiow_b200_scene_create(const rtiow_scene_desc_t* d, int device, rtiow_scene
     if (const char* env = std::getenv("RTIOW_B200_STAGING_MIB")) s->staging_mib = static_cast<uint32_t>(std::atoi(env));
     if (const char* env = std::getenv("RTIOW_B200_FORCE_GLOBAL")) s->force_global = std::atoi(env) != 0;
     if (const char* env = std::getenv("RTIOW_B200_TRAVERSAL")) s->traversal = std::min(2, std::max(0, std::atoi(env)));
+    if (const char* env = std::getenv("RTIOW_B200_REFILL_LANES")) s->refill_lanes = static_cast<uint32_t>(std::min(32, std::max(0, std::atoi(env))));
     if (const char* env = std::getenv("RTIOW_B200_SAMPLE_CHUNK")) s->sample_chunk = static_cast<uint32_t>(std::max(0, std::atoi(env)));
     {   // build + upload the blob of the selected traversal now, so that render calls only launch
         const rtiow::BlobMode mode = s->traversal == RTIOW_TRAVERSAL_REFERENCE_ORDER ? rtiow::kBlobReferenceOrder

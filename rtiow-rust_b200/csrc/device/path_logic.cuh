@@ -39,6 +39,7 @@ struct KParams {
     uint32_t key0, key1;
     uint32_t bg_kind;
     float bg0[3], bg1[3];
+    uint32_t refill_thr;        // idle lanes are handed new pixel-samples once this many of a warp wait (>= 1)
     float4* staging;            // [s_count][npix] {r, g, b, segments}
     unsigned int* work_counter;
 };

@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
         const bool need = !active;
         const uint32_t need_mask = __ballot_sync(0xffffffffu, need);
         bool fresh = false;
-        if (need_mask != 0u && !exhausted) {
+        // refill in batches: camera-ray generation costs the warp the same whether 3 or 30 lanes need it
+        if (!exhausted && (static_cast<uint32_t>(__popc(need_mask)) >= P.refill_thr || need_mask == 0xffffffffu)) {
             uint32_t my_rank = __popc(need_mask & lt_mask);
             uint32_t remaining = __popc(need_mask);
             for (;;) {
