@@ -342,8 +342,8 @@ static RT_HD_NOINLINE float shutter_time_retry(Rng rng, float scale, float toff,
     }
 }
 
-RT_HD void generate_camera_ray(const KParams& P, PathState& st) {
-    const uint32_t r = st.pix / P.nx, x = st.pix - r * P.nx;
+// (x, r) = column and packed row of st.pix.
+RT_HD void generate_camera_ray(const KParams& P, PathState& st, uint32_t x, uint32_t r) {
     const uint32_t band = r / P.row_band;
     const uint32_t y = P.ny - 1u - (P.row_begin + band * P.row_step + (r - band * P.row_band));  // (0..ny).rev()  lib.rs:326-330
     st.rng.pixel = y * P.nx + x;
@@ -591,11 +591,15 @@ RT_HD void trav_node_step_fast(const SceneT<Mem>& sc, Trav& tr, TravStack& stk) 
 // A leaf of the fast tree: the reference's Aabb::hit (aabb.rs:18-29) on the leaf's own box — the
 // BBOX item kept in front of its primitives — and then the primitives.
 template <class Mem, class Path>
-RT_HD void trav_leaf_step_fast(const SceneT<Mem>& sc, const Path& path, Trav& tr, const TravStack& stk) {  // requires trav_in_leaf(tr)
-    const uint32_t first = tr.cur & 0x00ffffffu;
+RT_HD void trav_leaf_visit_fast(const SceneT<Mem>& sc, const Path& path, Trav& tr, uint32_t link) {
+    const uint32_t first = link & 0x00ffffffu;
     const float4 mn = sc.item_a(first - 1u), mx = sc.item_b(first - 1u);
     float start;
-    if (slab_test(mn, mx, tr.fo, trav_exact_inv<true>(tr), tr.best_t, start)) trav_leaf_test(sc, path, tr, tr.cur);
+    if (slab_test(mn, mx, tr.fo, trav_exact_inv<true>(tr), tr.best_t, start)) trav_leaf_test(sc, path, tr, link);
+}
+template <class Mem, class Path>
+RT_HD void trav_leaf_step_fast(const SceneT<Mem>& sc, const Path& path, Trav& tr, const TravStack& stk) {  // requires trav_in_leaf(tr)
+    trav_leaf_visit_fast(sc, path, tr, tr.cur);
     trav_pop(tr, stk);
 }
 

@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
 
     // ---- per-lane path state ------------------------------------------------------------------
     bool active = false;
+    uint32_t fresh_x = 0, fresh_r = 0;
     PathState st;
     st.pix = 0; st.samp = 0; st.bounce = 0;
     st.ro = splat(0.f); st.rd = splat(0.f); st.strength = splat(1.f);
@@ -105,6 +106,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
                     if (x < P.nx && r < P.n_rows) {  // tiles on the right / bottom edge are partly outside
                         st.samp = P.s_begin + pool_s0 + (job >> 5);
                         st.pix = r * P.nx + x;
+                        fresh_x = x;
+                        fresh_r = r;
                         fresh = true;
                     }
                 }
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
             }
         }
         if (fresh) {
-            generate_camera_ray(P, st);
+            generate_camera_ray(P, st, fresh_x, fresh_r);
             active = true;
         }
         if (__ballot_sync(0xffffffffu, active) == 0u) break;

@@ -50,7 +50,7 @@ extern "C" __attribute__((visibility("default"))) int harness_render(const rtiow
             PathState st;
             st.pix = pix; st.samp = s;
             st.rng = Rng{P.key0, P.key1, 0u, 0u};
-            generate_camera_ray(P, st);
+            generate_camera_ray(P, st, pix % nx, pix / nx);
             V3 result;
             uint32_t segs;
             for (;;) {
