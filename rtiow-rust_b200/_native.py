@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-BUILD_DIR = os.path.join(_HERE, "_build")
+# RTIOW_B200_BUILD_DIR selects another in-tree build (`make OUT=_build_x`): same-box A/B timing of two kernels
+BUILD_DIR = os.path.join(_HERE, os.environ.get("RTIOW_B200_BUILD_DIR", "_build"))
 ABI_LIB = os.path.join(BUILD_DIR, "librtiow_b200.so")
 HOST_LIB = os.path.join(BUILD_DIR, "librtiow_host.so")
 
