@@ -679,27 +679,31 @@ RT_HD void trav_stream(const SceneT<Mem>& sc, const Path& path, Trav& tr) {
             tr.sp = 0;
             i = f2u(ia.w) >> 4;
             break;
-        } else if (kind == IT_BBOX) {  // Aabb::hit  aabb.rs:18-29
-            const float4 ib = sc.item_b(i);
-            float start;
-            i = slab_test(ia, ib, tr.fo, trav_exact_inv<kFast>(tr), tr.best_t, start) ? i + 1u : (f2u(ia.w) >> 4);
         } else if (kind == IT_SPHERE || kind == IT_RECT) {
             const float4 ib = sc.item_b(i);
             const uint32_t frame = f2u(ia.w) >> 4;
-            if (frame != tr.f_id && frame != pf_id) {
-                const uint2 fr = sc.frame(frame);
-                const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * (fr.x + tr.f_nops), fr.y - tr.f_nops, tr.fo, tr.fd, path.rtime());
-                po = r.o;
-                pd = r.d;
+            if (frame != pf_id) {  // (po, pd) = the ray in this primitive's frame; consecutive items mostly share it
+                if (frame == tr.f_id) {
+                    po = tr.fo;
+                    pd = tr.fd;
+                } else {
+                    const uint2 fr = sc.frame(frame);
+                    const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * (fr.x + tr.f_nops), fr.y - tr.f_nops, tr.fo, tr.fd, path.rtime());
+                    po = r.o;
+                    pd = r.d;
+                }
                 pf_id = frame;
             }
-            const bool own = frame != tr.f_id;
             float t;
-            if (prim_hit_t(sc, ia, ib, own ? po : tr.fo, own ? pd : tr.fd, path, frame, 0u, kNear, tr.best_t, t)) {
+            if (prim_hit_t(sc, ia, ib, po, pd, path, frame, 0u, kNear, tr.best_t, t)) {
                 tr.best_t = t;  // nearest = rec.t (lib.rs:42) / t_range.end = h.t (bvh.rs:98-100, object.rs:404-406)
                 tr.best = i;
             }
             i += 1u;
+        } else if (kind == IT_BBOX) {  // Aabb::hit  aabb.rs:18-29
+            const float4 ib = sc.item_b(i);
+            float start;
+            i = slab_test(ia, ib, tr.fo, trav_exact_inv<kFast>(tr), tr.best_t, start) ? i + 1u : (f2u(ia.w) >> 4);
         } else if (kind == IT_MEDIUM) {
             const BestHit h = medium_hit(sc, path.rng(), path.bounce(), path.rtime(), i, tr.fo, tr.fd, tr.f_id, tr.f_nops, tr.best_t, tr.best);
             tr.best_t = h.t;
