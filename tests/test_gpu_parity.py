@@ -209,3 +209,19 @@ def test_c2_full_size_properties(oracle):
     halves = [R.par_cast(nx, ny, ns, cam, world, rows=(0, 400)).rgb, R.par_cast(nx, ny, ns, cam, world, rows=(400, 800)).rgb]
     assert bits_equal(np.concatenate(halves), full)   # sharding is exact
     assert 2.0 < st["segments"] / st["samples"] < 3.2
+
+
+def test_philox_core_matches_curand(tmp_path):
+    """The RNG core of the render path (rt_math.cuh philox4x32_10) against NVIDIA's independent implementation
+    (curand_Philox4x32_10) on 4 M (counter, key) pairs: pins the generator to something that is not ours."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available on this box")
+    exe = str(tmp_path / "philox_vs_curand")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-o", exe,
+                           os.path.join(os.path.dirname(os.path.abspath(__file__)), "cuda", "philox_vs_curand.cu")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "0 mismatching words" in out.stdout
