@@ -148,6 +148,7 @@ struct Compactor {
     std::vector<AccelNode> nodes;
     uint32_t n_accel = 0;
     int max_depth = 0;
+    bool odd_nesting = false;  // a skip link that leaves its enclosing box: the stream is shipped as it is
 
     uint32_t kind(uint32_t i) const { return d->items[i].a_w & 15u; }
     uint32_t payload(uint32_t i) const { return d->items[i].a_w >> 4; }
@@ -175,7 +176,7 @@ struct Compactor {
 
     void run(uint32_t begin, uint32_t end) {
         uint32_t i = begin;
-        while (i < end) {
+        while (i < end && !odd_nesting) {
             const uint32_t k = kind(i);
             if (k == RTIOW_ITEM_BBOX) {
                 const uint32_t s = payload(i);
@@ -213,9 +214,8 @@ struct Compactor {
                     run(i + 1, s);
                     out[at].a_w = RTIOW_ITEM_BBOX | (static_cast<uint32_t>(out.size()) << 4);
                     i = s;
-                } else {  // improperly nested skip link (validated to be forward): copy verbatim region
-                    // cannot happen for streams produced by the flatteners; keep semantics by disabling compaction
-                    throw 0;
+                } else {  // improperly nested skip link (validated to be forward): cannot happen for streams
+                    odd_nesting = true;  // produced by the flatteners; keep semantics by disabling compaction
                 }
             } else if (k == RTIOW_ITEM_MEDIUM) {
                 out.push_back(d->items[i]);
@@ -246,9 +246,8 @@ inline std::vector<unsigned char> build_blob(const rtiow_scene_desc_t* d, bool u
         return static_cast<uint32_t>(off);
     };
     blob_detail::Compactor cp{d, enable_accel, mode == kBlobFast, {}, {}};
-    try {
-        cp.run(0, d->n_items);
-    } catch (int) {  // odd nesting: ship the stream as it is
+    cp.run(0, d->n_items);
+    if (cp.odd_nesting) {  // ship the stream as it is
         cp = blob_detail::Compactor{d, false, false, {}, {}};
         cp.out.assign(d->items, d->items + d->n_items);
     }
