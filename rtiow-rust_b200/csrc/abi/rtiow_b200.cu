@@ -332,8 +332,8 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var.fn, var.threads, dyn_smem));
     if (occ < 1) return set_err(RTIOW_ERR_CUDA, "render kernel does not fit on an SM");
     if (s->ctas_per_sm) occ = std::min<int>(occ, static_cast<int>(s->ctas_per_sm));
-    const uint32_t tiles_x = (nx + 7u) / 8u;
-    const uint32_t n_groups = tiles_x * ((n_rows + 3u) / 4u);  // 8x4-pixel tiles
+    const uint32_t tiles_x = (nx + rtiow::kTileW - 1u) / rtiow::kTileW;
+    const uint32_t n_groups = tiles_x * ((n_rows + rtiow::kTileH - 1u) / rtiow::kTileH);  // 8x4-pixel tiles
     uint32_t grid = static_cast<uint32_t>(s->sm_count) * static_cast<uint32_t>(occ);
     const uint32_t warps_per_cta = static_cast<uint32_t>(var.threads) / 32u;
     grid = std::max(1u, std::min(grid, (n_groups + warps_per_cta - 1) / warps_per_cta));

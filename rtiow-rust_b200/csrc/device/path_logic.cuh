@@ -11,6 +11,11 @@
 
 namespace rtiow {
 
+// work tiles of the megakernel: kTileW x kTileH = 32 pixels (render_kernel.cuh); kTileW = 1 << kTileWLog2
+#ifndef RT_TILE_W_LOG2
+#define RT_TILE_W_LOG2 3
+#endif
+constexpr uint32_t kTileWLog2 = RT_TILE_W_LOG2, kTileW = 1u << kTileWLog2, kTileH = 32u / kTileW;
 constexpr float kNear = 0.001f;               // lib.rs:35,53
 constexpr float kF32Max = 3.402823466e+38f;   // std::f32::MAX
 constexpr float kF32Min = -3.402823466e+38f;  // std::f32::MIN

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
                 if (need && !fresh && my_rank < avail) {
                     // job = sample-major over the tile: 32 neighbouring pixels of one sample first
                     const uint32_t job = pool_next + my_rank;
-                    const uint32_t x = pool_x0 + (job & 7u), r = pool_r0 + ((job >> 3) & 3u);
+                    const uint32_t x = pool_x0 + (job & (kTileW - 1u)), r = pool_r0 + ((job >> kTileWLog2) & (kTileH - 1u));
                     if (x < P.nx && r < P.n_rows) {  // tiles on the right / bottom edge are partly outside
                         st.samp = P.s_begin + pool_s0 + (job >> 5);
                         st.pix = r * P.nx + x;
@@ -123,8 +123,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
                 // unit u = samples [c * s_chunk, ...) of tile g; small units keep the tail short
                 const uint32_t g = u / P.n_chunks, c = u - g * P.n_chunks;
                 const uint32_t ty = g / P.tiles_x;
-                pool_x0 = (g - ty * P.tiles_x) * 8u;
-                pool_r0 = ty * 4u;
+                pool_x0 = (g - ty * P.tiles_x) * kTileW;
+                pool_r0 = ty * kTileH;
                 pool_s0 = c * P.s_chunk;
                 const uint32_t s_n = P.s_count - pool_s0 < P.s_chunk ? P.s_count - pool_s0 : P.s_chunk;
                 pool_next = 0u;
