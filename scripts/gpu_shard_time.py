@@ -9,7 +9,7 @@ nx, ny, ns = 1200, 800, 50
 w, c = R.build_scene("book1", nx, ny, use_bvh=True)
 out = torch.empty((ny, nx, 3), dtype=torch.float32, device="cuda")
 t1 = None
-for G, B in ((1, 1), (2, 1), (2, 4), (4, 1), (4, 4), (8, 1), (8, 4), (8, 8)):
+for G, B in ((1, 4), (2, 4), (4, 4), (8, 4)):
     for rank in sorted({0, G - 1}):
         best = 1e9
         for _ in range(4):
