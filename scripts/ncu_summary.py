@@ -44,7 +44,8 @@ def to_bytes(m):
 
 
 dram = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
-with open(os.path.join(ROOT, "profiles", "ncu_summary.json"), "w") as f:
+# profiles/ncu_summary.json feeds bench.py's roofline.traffic: only a capture of the headline workload (C2) may refresh it
+with open(os.path.join(ROOT, "profiles", "ncu_summary.json") if not os.environ.get("NCU_SUMMARY_KEEP") else os.devnull, "w") as f:
     json.dump({"render_kernel_dram_bytes_per_launch": dram, "source": os.path.relpath(prefix + "_render_kernel_ncu_full.json", ROOT),
                "kernel_ms_under_ncu": float(out["gpu__time_duration.sum"]["value"])}, f, indent=1)
 if len(sys.argv) > 4:
