@@ -354,6 +354,12 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     std::memcpy(P.bg0, s->bg0, 12); std::memcpy(P.bg1, s->bg1, 12);
     P.staging = static_cast<float4*>(W.staging.p);
     P.work_counter = W.d_counter;
+    // Scenes whose segments run through a lot of different code (media, wrapper frames, nested subtrees) are
+    // bound by instruction fetch: ncu shows `no_instruction` as the top stall with the 99 % hot set at 35 KB against
+    // a 32 KB L1.5 I-cache.  Two CTA barriers per round (before hit_top, before shading) keep the 24 warps in the
+    // same phase, i.e. the same few KB of code: final scene +16 %; book-1 and Cornell, whose hot set fits, lose 8-30 %.
+    P.phase_sync = std::getenv("RTIOW_B200_PHASE_SYNC") ? static_cast<uint32_t>(std::atoi(std::getenv("RTIOW_B200_PHASE_SYNC")))
+                                                         : (s->costly_segments ? 2u : 0u);
     // Idle lanes get new pixel-samples once `refill_thr` lanes of the warp wait: generating camera rays costs the
     // warp the same for 3 lanes as for 30, and rays started together stay coherent.  Waiting costs idle lane
     // iterations, which are expensive in scenes with media / wrapper frames and frequent where paths are short.

@@ -45,6 +45,7 @@ struct KParams {
     uint32_t bg_kind;
     float bg0[3], bg1[3];
     uint32_t refill_thr;        // idle lanes are handed new pixel-samples once this many of a warp wait (>= 1)
+    uint32_t phase_sync;        // CTA barriers per round: 1 = before hit_top, 2 = also before shading (code-fetch locality)
     float4* staging;            // [s_count][npix] {r, g, b, segments}
     unsigned int* work_counter;
 };

@@ -135,12 +135,21 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
             generate_camera_ray(P, st, fresh_x, fresh_r);
             active = true;
         }
-        if (__ballot_sync(0xffffffffu, active) == 0u) break;
+        const bool warp_alive = __ballot_sync(0xffffffffu, active) != 0u;
+        if (P.phase_sync != 0u) {
+            // all warps of the CTA enter hit_top together (and leave the kernel together): their instruction
+            // fetches then hit the same few KB of code instead of the whole kernel
+            if (!__syncthreads_or(warp_alive ? 1 : 0)) break;
+        } else if (!warp_alive) {
+            break;
+        }
 
+        // ============ 2. World::hit_top ============================================================
+        float best_t = 0.f;
+        uint32_t best = kNoHit;
+        if (active) best = hit_top_stream<kFrames, kFast>(sc, st, best_t);
+        if (P.phase_sync == 2u) __syncthreads();
         if (active) {
-            // ============ 2. World::hit_top ========================================================
-            float best_t;
-            const uint32_t best = hit_top_stream<kFrames, kFast>(sc, st, best_t);
             // ============ 3. emitted + scatter =====================================================
             const uint32_t segs = st.bounce + 1u;
             V3 result;
