@@ -358,8 +358,15 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     // bound by instruction fetch: ncu shows `no_instruction` as the top stall with the 99 % hot set at 35 KB against
     // a 32 KB L1.5 I-cache.  Two CTA barriers per round (before hit_top, before shading) keep the 24 warps in the
     // same phase, i.e. the same few KB of code: final scene +16 %; book-1 and Cornell, whose hot set fits, lose 8-30 %.
+    // Named barriers over half the CTA (12 warps) wait a little less than __syncthreads and keep the locality.
     P.phase_sync = std::getenv("RTIOW_B200_PHASE_SYNC") ? static_cast<uint32_t>(std::atoi(std::getenv("RTIOW_B200_PHASE_SYNC")))
                                                          : (s->costly_segments ? 2u : 0u);
+    P.phase_group = static_cast<uint32_t>(var.threads) / 32u;
+    if (P.phase_sync != 0u && P.phase_group % 2u == 0u) P.phase_group /= 2u;  // two barrier groups per CTA: measured best
+    if (const char* env = std::getenv("RTIOW_B200_PHASE_GROUP")) {
+        const uint32_t g = static_cast<uint32_t>(std::max(1, std::atoi(env)));
+        if (P.phase_group % g == 0 && P.phase_group / g <= 15) P.phase_group = g;
+    }
     // Idle lanes get new pixel-samples once `refill_thr` lanes of the warp wait: generating camera rays costs the
     // warp the same for 3 lanes as for 30, and rays started together stay coherent.  Waiting costs idle lane
     // iterations, which are expensive in scenes with media / wrapper frames and frequent where paths are short.

@@ -136,10 +136,20 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
             active = true;
         }
         const bool warp_alive = __ballot_sync(0xffffffffu, active) != 0u;
+        const uint32_t bar_id = 1u + (threadIdx.x >> 5) / P.phase_group, bar_threads = P.phase_group * 32u;
         if (P.phase_sync != 0u) {
-            // all warps of the CTA enter hit_top together (and leave the kernel together): their instruction
-            // fetches then hit the same few KB of code instead of the whole kernel
-            if (!__syncthreads_or(warp_alive ? 1 : 0)) break;
+            // the warps of a barrier group enter hit_top together (and leave the kernel together): their
+            // instruction fetches then hit the same few KB of code instead of the whole kernel
+            uint32_t any;
+            asm volatile(
+                "{\n\t.reg .pred p, q;\n\t"
+                "setp.ne.u32 q, %3, 0;\n\t"
+                "bar.red.or.pred p, %1, %2, q;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(any)
+                : "r"(bar_id), "r"(bar_threads), "r"(warp_alive ? 1u : 0u)
+                : "memory");
+            if (any == 0u) break;
         } else if (!warp_alive) {
             break;
         }
@@ -148,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
         float best_t = 0.f;
         uint32_t best = kNoHit;
         if (active) best = hit_top_stream<kFrames, kFast>(sc, st, best_t);
-        if (P.phase_sync == 2u) __syncthreads();
+        if (P.phase_sync == 2u) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
         if (active) {
             // ============ 3. emitted + scatter =====================================================
             const uint32_t segs = st.bounce + 1u;
