@@ -179,6 +179,7 @@ typedef struct rtiow_stats_t {
     uint32_t accel_nodes;    /* nodes of the library's own index over the scene's Bvh subtrees (0 = none) */
     uint32_t accel_subtrees; /* how many Bvh subtrees were re-indexed                                      */
     uint32_t traversal;      /* RTIOW_TRAVERSAL_*: how the last render walked Bvh subtrees                 */
+    uint32_t lean_kernel;    /* 1 if the last render used the spheres-only specialisation of the megakernel */
 } rtiow_stats_t;
 
 typedef struct rtiow_scene rtiow_scene_t;
@@ -237,6 +238,12 @@ RTIOW_API int rtiow_b200_get_stats(rtiow_scene_t* scene, rtiow_stats_t* out);
  * force_global != 0 keeps the scene in global memory even if it fits shared memory. */
 RTIOW_API int rtiow_b200_set_tuning(rtiow_scene_t* scene, uint32_t cta_threads, uint32_t ctas_per_sm, uint32_t staging_mib,
                           int force_global);
+
+/* The megakernel is compiled twice: for any scene, and for scenes that hold nothing but unwrapped spheres with
+ * Lambertian / Metal / Dielectric materials and constant textures (book-1's random_scene) — the same per-path
+ * code with everything else compiled out: half the instructions, no register spills.  Picked automatically
+ * from the scene's content; enable = 0 forces the general kernel.  Same image either way. */
+RTIOW_API int rtiow_b200_set_specialisation(rtiow_scene_t* scene, int enable);
 
 /* How `Bvh` subtrees (src/bvh.rs) are walked.  All give the same image bit for bit; the choice is
  * speed only.  REINDEXED (default): the library indexes the subtree's leaves with its own tree,

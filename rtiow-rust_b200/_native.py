@@ -60,14 +60,14 @@ class Stats(C.Structure):
                 ("segments", C.c_uint64), ("kernel_launches", C.c_uint32), ("passes", C.c_uint32),
                 ("scene_in_smem", C.c_uint32), ("scene_bytes", C.c_uint32), ("grid", C.c_uint32),
                 ("block", C.c_uint32), ("dyn_smem_bytes", C.c_uint32), ("regs_per_thread", C.c_uint32),
-                ("accel_nodes", C.c_uint32), ("accel_subtrees", C.c_uint32), ("traversal", C.c_uint32)]
+                ("accel_nodes", C.c_uint32), ("accel_subtrees", C.c_uint32), ("traversal", C.c_uint32), ("lean_kernel", C.c_uint32)]
 
 
 # every symbol include/rtiow_b200.h declares
 ABI_SYMBOLS = ("rtiow_b200_abi_version", "rtiow_b200_last_error", "rtiow_b200_scene_validate",
                "rtiow_b200_scene_create", "rtiow_b200_scene_destroy", "rtiow_b200_release_cached_memory", "rtiow_b200_render", "rtiow_b200_render_rows",
                "rtiow_b200_render_rows_device", "rtiow_b200_render_rows_strided_device", "rtiow_b200_render_samples", "rtiow_b200_ppm_quantise",
-               "rtiow_b200_get_stats", "rtiow_b200_set_tuning", "rtiow_b200_set_traversal")
+               "rtiow_b200_get_stats", "rtiow_b200_set_tuning", "rtiow_b200_set_traversal", "rtiow_b200_set_specialisation")
 
 _abi = None
 _host = None
@@ -102,6 +102,7 @@ def abi():
         L.rtiow_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.rtiow_b200_set_tuning.argtypes = [vp, u32, u32, u32, C.c_int]
         L.rtiow_b200_set_traversal.argtypes = [vp, C.c_int]
+        L.rtiow_b200_set_specialisation.argtypes = [vp, C.c_int]
         _abi = L
     return _abi
 

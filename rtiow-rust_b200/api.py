@@ -137,6 +137,10 @@ class World:
     def set_tuning(self, device=0, cta_threads=0, ctas_per_sm=0, staging_mib=0, force_global=False):
         _check(N.abi().rtiow_b200_set_tuning(self.gpu(device), cta_threads, ctas_per_sm, staging_mib, int(force_global)))
 
+    def set_specialisation(self, enable=True, device=0):
+        """False forces the general megakernel even if the scene qualifies for the spheres-only one.  Same image."""
+        _check(N.abi().rtiow_b200_set_specialisation(self.gpu(device), int(bool(enable))))
+
     def set_traversal(self, mode, device=0):
         """0 = re-indexed Bvh subtrees, conservative inner box test (default); 1 = the reference's own visiting
         order; 2 = re-indexed with the reference's box test at every node.  Same image every way."""

@@ -15,7 +15,7 @@ struct KernelVariant {
 };
 
 // render_kernel (render_kernel.cuh): one path per lane.  threads in {256, 512, 768}.
-KernelVariant pick_plain_smem(bool frames, bool fast, uint32_t threads);
-KernelVariant pick_plain_global(bool frames, bool fast, uint32_t threads);
+KernelVariant pick_plain_smem(bool frames, bool fast, bool lean, uint32_t threads);
+KernelVariant pick_plain_global(bool frames, bool fast, bool lean, uint32_t threads);
 
 }  // namespace rtiow

@@ -239,6 +239,8 @@ struct rtiow_scene {
     // tuning
     uint32_t cta_threads = 0, ctas_per_sm = 0, staging_mib = 2048, sample_chunk = 0;
     bool force_global = false;
+    bool lean_scene = false;       // only world-frame spheres, Lambertian / Metal / Dielectric, constant textures
+    bool specialise = true;        // use the lean kernel for lean scenes (same image, fewer instructions)
     uint32_t refill_lanes = 0;     // 0 = automatic
     bool costly_segments = false;  // the scene has wrapper frames on subtrees or constant media
 
@@ -324,7 +326,9 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     const bool smem = B.bytes <= smem_cap && !s->force_global;
     // 0 = automatic: 768 threads (80 registers) per CTA, one CTA per SM
     const uint32_t threads = s->cta_threads ? s->cta_threads : 768u;
-    const KernelVariant var = smem ? rtiow::pick_plain_smem(s->has_frames, fast, threads) : rtiow::pick_plain_global(s->has_frames, fast, threads);
+    const bool lean = s->lean_scene && s->specialise;
+    const KernelVariant var = smem ? rtiow::pick_plain_smem(s->has_frames, fast, lean, threads)
+                                   : rtiow::pick_plain_global(s->has_frames, fast, lean, threads);
     if (!var.fn) return set_err(RTIOW_ERR_INVALID_ARG, "no kernel instantiation for this cta_threads");
     const size_t dyn_smem = smem ? B.bytes : 0;
     CK(cudaFuncSetAttribute(var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem)));
@@ -431,6 +435,7 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     s->stats.block = static_cast<uint32_t>(var.threads);
     s->stats.dyn_smem_bytes = static_cast<uint32_t>(dyn_smem);
     s->stats.regs_per_thread = static_cast<uint32_t>(fa.numRegs);
+    s->stats.lean_kernel = lean ? 1u : 0u;
     s->stats.traversal = static_cast<uint32_t>(mode == rtiow::kBlobFast ? RTIOW_TRAVERSAL_REINDEXED
                                                : (mode == rtiow::kBlobExact ? RTIOW_TRAVERSAL_REINDEXED_EXACT : RTIOW_TRAVERSAL_REFERENCE_ORDER));
     return RTIOW_OK;
@@ -480,6 +485,7 @@ int rtiow_b200_scene_create(const rtiow_scene_desc_t* d, int device, rtiow_scene
     s->has_frames = has_frames;
     s->costly_segments = has_frames;
     for (uint32_t i = 0; i < d->n_items; ++i) s->costly_segments |= (d->items[i].a_w & 15u) == RTIOW_ITEM_MEDIUM;
+    s->lean_scene = rtiow::lean_scene(d);
     s->bg_kind = d->background_kind;
     std::memcpy(s->bg0, d->background_c0, 12);
     std::memcpy(s->bg1, d->background_c1, 12);
@@ -498,6 +504,7 @@ int rtiow_b200_scene_create(const rtiow_scene_desc_t* d, int device, rtiow_scene
     if (const char* env = std::getenv("RTIOW_B200_STAGING_MIB")) s->staging_mib = static_cast<uint32_t>(std::atoi(env));
     if (const char* env = std::getenv("RTIOW_B200_FORCE_GLOBAL")) s->force_global = std::atoi(env) != 0;
     if (const char* env = std::getenv("RTIOW_B200_TRAVERSAL")) s->traversal = std::min(2, std::max(0, std::atoi(env)));
+    if (const char* env = std::getenv("RTIOW_B200_SPECIALISE")) s->specialise = std::atoi(env) != 0;
     if (const char* env = std::getenv("RTIOW_B200_REFILL_LANES")) s->refill_lanes = static_cast<uint32_t>(std::min(32, std::max(0, std::atoi(env))));
     if (const char* env = std::getenv("RTIOW_B200_SAMPLE_CHUNK")) s->sample_chunk = static_cast<uint32_t>(std::max(0, std::atoi(env)));
     {   // build + upload the blob of the selected traversal now, so that render calls only launch
@@ -541,6 +548,12 @@ int rtiow_b200_set_tuning(rtiow_scene_t* s, uint32_t cta_threads, uint32_t ctas_
     s->ctas_per_sm = ctas_per_sm;
     if (staging_mib) s->staging_mib = staging_mib;
     s->force_global = force_global != 0;
+    return RTIOW_OK;
+}
+
+int rtiow_b200_set_specialisation(rtiow_scene_t* s, int enable) {
+    if (!s) return set_err(RTIOW_ERR_INVALID_ARG, "null scene");
+    s->specialise = enable != 0;
     return RTIOW_OK;
 }
 

@@ -125,6 +125,25 @@ inline int validate_desc(const rtiow_scene_desc_t* d, bool* has_frames, bool* us
 // How Bvh subtrees are laid out for the device (rtiow_b200.h RTIOW_TRAVERSAL_*).
 enum BlobMode { kBlobFast = 0, kBlobReferenceOrder = 1, kBlobExact = 2 };
 
+// Can the spheres-only kernel specialisation render this scene?  (path_logic.cuh SceneT<Mem, kLean>)
+inline bool lean_scene(const rtiow_scene_desc_t* d) {
+    for (uint32_t i = 0; i < d->n_items; ++i) {
+        const uint32_t kind = d->items[i].a_w & 15u, payload = d->items[i].a_w >> 4;
+        if (kind == RTIOW_ITEM_SPHERE) {
+            if (payload != 0) return false;                                  // a wrapper chain
+            if (((d->items[i].b_w >> 24) & RTIOW_FLAG_FLIP) != 0) return false;
+        } else if (kind != RTIOW_ITEM_BBOX && kind != RTIOW_ITEM_END) {
+            return false;                                                        // rects, media, frame switches
+        }
+    }
+    for (uint32_t m = 0; m < d->n_materials; ++m) {
+        const rtiow_material_t& mt = d->materials[m];
+        if (mt.kind > RTIOW_MAT_DIELECTRIC) return false;                        // lights, Isotropic
+        if (mt.kind == RTIOW_MAT_LAMBERTIAN && d->textures[mt.tex].kind != RTIOW_TEX_CONSTANT) return false;
+    }
+    return true;
+}
+
 struct BlobLayout {
     uint32_t off_nodes, off_frames, off_ops, off_mats, off_tex, off_pvecs, off_pperm;
     uint32_t off_fnodes;

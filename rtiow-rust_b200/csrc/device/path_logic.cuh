@@ -90,9 +90,12 @@ struct MemGlobal {
 };
 #endif
 
-// Views into the scene blob.
-template <class Mem>
+// Views into the scene blob.  kLean: the scene holds nothing but world-frame spheres with Lambertian / Metal /
+// Dielectric materials and constant textures (rtiow_b200.cu lean_scene()), so rects, wrapper chains, media,
+// lights, Isotropic and procedural textures compile out of the megakernel: half the code, no register spills.
+template <class Mem, bool kLean = false>
 struct SceneT {
+    static constexpr bool lean = kLean;
     Mem m;
     uint32_t off_nodes, off_frames, off_ops, off_mats, off_tex, off_pvecs, off_pperm, off_fnodes;
     RT_HD float4 item_a(uint32_t i) const { return m.ld4(32u * i); }
@@ -106,9 +109,9 @@ struct SceneT {
     RT_HD uint32_t pperm(uint32_t i) const { return m.ld1b(off_pperm + i); }
 };
 
-template <class Mem>
-RT_HD SceneT<Mem> scene_views(Mem m, const KParams& P) {
-    SceneT<Mem> sc;
+template <bool kLean, class Mem>
+RT_HD SceneT<Mem, kLean> scene_views(Mem m, const KParams& P) {
+    SceneT<Mem, kLean> sc;
     sc.m = m;
     sc.off_nodes = P.off_nodes; sc.off_frames = P.off_frames; sc.off_ops = P.off_ops; sc.off_mats = P.off_mats;
     sc.off_tex = P.off_tex; sc.off_pvecs = P.off_pvecs; sc.off_pperm = P.off_pperm;
@@ -244,12 +247,16 @@ RT_HD bool rect_hit_t(V3 o, V3 d, uint32_t axis, float4 ia, float4 ib, float t_l
 // Any primitive item against a ray (o, d) that is already in frame `cur_frame` (whose chain has
 // `cur_nops` ops, a prefix of the item's own chain): the item's remaining wrappers are applied
 // first, exactly like the nested Object::hit calls.
-template <class Mem, class Path>
-RT_HD bool prim_hit_t(const SceneT<Mem>& sc, float4 ia, float4 ib, V3 o, V3 d, const Path& path, uint32_t cur_frame,
+template <class Mem, bool kLean, class Path>
+RT_HD bool prim_hit_t(const SceneT<Mem, kLean>& sc, float4 ia, float4 ib, V3 o, V3 d, const Path& path, uint32_t cur_frame,
                       uint32_t cur_nops, float t_lo, float t_hi, float& t_out) {
     const uint32_t kind = f2u(ia.w) & 15u;
     const uint32_t frame = f2u(ia.w) >> 4;
     const uint32_t flags = f2u(ib.w) >> 24;
+    if (kLean) {  // a world-frame sphere, nothing else exists in the scene
+        if (flags & FL_HAS_OFFSET) o = o - mk(ib.x, ib.y, ib.z);
+        return sphere_hit_t(o, d, ia.x, t_lo, t_hi, t_out);
+    }
     if (frame != cur_frame) {
         const uint2 fr = sc.frame(frame);
         const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * (fr.x + cur_nops), fr.y - cur_nops, o, d, path.rtime());
@@ -266,8 +273,8 @@ RT_HD bool prim_hit_t(const SceneT<Mem>& sc, float4 ia, float4 ib, V3 o, V3 d, c
 // ------------------------------------------------------------------------------------------------
 // Textures (texture.rs) and Perlin noise (perlin.rs)
 // ------------------------------------------------------------------------------------------------
-template <class Mem>
-RT_HD_NOINLINE float perlin_noise(const SceneT<Mem>& sc, V3 p) {  // perlin.rs:49-64 + trilinear_interp :31-47
+template <class Mem, bool kLean>
+RT_HD_NOINLINE float perlin_noise(const SceneT<Mem, kLean>& sc, V3 p) {  // perlin.rs:49-64 + trilinear_interp :31-47
     const V3 ijk = mk(floorf(p.x), floorf(p.y), floorf(p.z));
     const V3 uvw = p - ijk;
     const int bi = f2i_rz_sat(ijk.x), bj = f2i_rz_sat(ijk.y), bk = f2i_rz_sat(ijk.z);  // `as i32`
@@ -292,8 +299,8 @@ RT_HD_NOINLINE float perlin_noise(const SceneT<Mem>& sc, V3 p) {  // perlin.rs:4
     return accum;
 }
 
-template <class Mem>
-RT_HD_NOINLINE float perlin_turb(const SceneT<Mem>& sc, V3 p) {  // perlin.rs:66-75 with depth 7 (texture.rs:24)
+template <class Mem, bool kLean>
+RT_HD_NOINLINE float perlin_turb(const SceneT<Mem, kLean>& sc, V3 p) {  // perlin.rs:66-75 with depth 7 (texture.rs:24)
     float accum = 0.f, weight = 1.f;
     for (int i = 0; i < 7; ++i) {
         accum += weight * perlin_noise(sc, p);
@@ -303,8 +310,8 @@ RT_HD_NOINLINE float perlin_turb(const SceneT<Mem>& sc, V3 p) {  // perlin.rs:66
     return fabsf(accum);
 }
 
-template <class Mem>
-RT_HD_NOINLINE V3 texture_eval(const SceneT<Mem>& sc, uint32_t id, V3 p) {
+template <class Mem, bool kLean>
+RT_HD_NOINLINE V3 texture_eval(const SceneT<Mem, kLean>& sc, uint32_t id, V3 p) {
     for (;;) {
         const float4 t0 = sc.tex(id, 0u);
         const uint32_t kind = f2u(t0.x);
@@ -318,10 +325,10 @@ RT_HD_NOINLINE V3 texture_eval(const SceneT<Mem>& sc, uint32_t id, V3 p) {
 }
 
 // Material's texture at p; constant textures were baked into the material record at scene upload.
-template <class Mem>
-RT_HD V3 material_texture(const SceneT<Mem>& sc, float4 m0, float4 m1, V3 p) {
+template <class Mem, bool kLean>
+RT_HD V3 material_texture(const SceneT<Mem, kLean>& sc, float4 m0, float4 m1, V3 p) {
     const uint32_t texkind = (f2u(m0.x) >> 8) & 0xffu;
-    if (texkind == TEX_CONSTANT) return mk(m1.x, m1.y, m1.z);
+    if (kLean || texkind == TEX_CONSTANT) return mk(m1.x, m1.y, m1.z);
     return texture_eval(sc, f2u(m0.y), p);
 }
 
@@ -469,8 +476,8 @@ RT_HD void trav_pop(Trav& tr, const TravStack& stk) {
 // smallest t, and among equal t the item that comes first in the reference's visiting order, which
 // is what `t < t_range.end` with a shrinking end gives in Bvh::hit (bvh.rs:94-106).
 // ------------------------------------------------------------------------------------------------
-template <class Mem>
-RT_HD void trav_node_step(const SceneT<Mem>& sc, Trav& tr, TravStack& stk) {  // requires trav_in_node(tr)
+template <class Mem, bool kLean>
+RT_HD void trav_node_step(const SceneT<Mem, kLean>& sc, Trav& tr, TravStack& stk) {  // requires trav_in_node(tr)
     const uint32_t n = tr.cur;
     const float4 q0 = sc.node_q(n, 0u), q1 = sc.node_q(n, 1u);
     const float4 q2 = sc.node_q(n, 2u), q3 = sc.node_q(n, 3u);
@@ -491,8 +498,8 @@ RT_HD void trav_node_step(const SceneT<Mem>& sc, Trav& tr, TravStack& stk) {  //
     }
 }
 
-template <class Mem, class Path>
-RT_HD void trav_leaf_test(const SceneT<Mem>& sc, const Path& path, Trav& tr, uint32_t link) {
+template <class Mem, bool kLean, class Path>
+RT_HD void trav_leaf_test(const SceneT<Mem, kLean>& sc, const Path& path, Trav& tr, uint32_t link) {
     const uint32_t first = link & 0x00ffffffu, count = (link >> 24) & 0x7fu;
     for (uint32_t j = first; j < first + count; ++j) {
         const float4 ia = sc.item_a(j), ib = sc.item_b(j);
@@ -504,8 +511,8 @@ RT_HD void trav_leaf_test(const SceneT<Mem>& sc, const Path& path, Trav& tr, uin
         }
     }
 }
-template <class Mem, class Path>
-RT_HD void trav_leaf_step(const SceneT<Mem>& sc, const Path& path, Trav& tr, const TravStack& stk) {  // requires trav_in_leaf(tr)
+template <class Mem, bool kLean, class Path>
+RT_HD void trav_leaf_step(const SceneT<Mem, kLean>& sc, const Path& path, Trav& tr, const TravStack& stk) {  // requires trav_in_leaf(tr)
     trav_leaf_test(sc, path, tr, tr.cur);
     trav_pop(tr, stk);
 }
@@ -540,8 +547,8 @@ RT_HD float rt_max3(float a, float b, float c) { return rt_max(rt_max(a, b), c);
 RT_HD float rt_min3(float a, float b, float c) { return rt_min(rt_min(a, b), c); }
 
 // Call after tr.fo / tr.fd / tr.inv are set (trav_begin, SET_FRAME).
-template <class Mem>
-RT_HD void trav_fast_setup(const SceneT<Mem>& sc, Trav& tr) {
+template <class Mem, bool kLean>
+RT_HD void trav_fast_setup(const SceneT<Mem, kLean>& sc, Trav& tr) {
     const float lo = 7.8886090522101181e-31f, hi = 1.2676506002282294e+30f;  // 2^-100, 2^100
     const float ax = fabsf(tr.inv.x), ay = fabsf(tr.inv.y), az = fabsf(tr.inv.z);
     const float om = rt_max3(fabsf(tr.fo.x), fabsf(tr.fo.y), fabsf(tr.fo.z));
@@ -568,8 +575,8 @@ RT_HD V3 trav_exact_inv(const Trav& tr) {
     return tr.inv;
 }
 
-template <class Mem>
-RT_HD void trav_node_step_fast(const SceneT<Mem>& sc, Trav& tr, TravStack& stk) {  // requires trav_in_node(tr)
+template <class Mem, bool kLean>
+RT_HD void trav_node_step_fast(const SceneT<Mem, kLean>& sc, Trav& tr, TravStack& stk) {  // requires trav_in_node(tr)
     const uint32_t nb = tr.cur * kFastNodeBytes;
     const float4 X = sc.m.ld4(tr.nbx + nb), Y = sc.m.ld4(tr.nby + nb), Z = sc.m.ld4(tr.nbz + nb);  // {near0, far0, near1, far1}
     const float4 L = sc.m.ld4(sc.off_fnodes + 96u + nb);                                            // {link0, link1, m, -}
@@ -597,23 +604,23 @@ RT_HD void trav_node_step_fast(const SceneT<Mem>& sc, Trav& tr, TravStack& stk) 
 
 // A leaf of the fast tree: the reference's Aabb::hit (aabb.rs:18-29) on the leaf's own box — the
 // BBOX item kept in front of its primitives — and then the primitives.
-template <class Mem, class Path>
-RT_HD void trav_leaf_visit_fast(const SceneT<Mem>& sc, const Path& path, Trav& tr, uint32_t link) {
+template <class Mem, bool kLean, class Path>
+RT_HD void trav_leaf_visit_fast(const SceneT<Mem, kLean>& sc, const Path& path, Trav& tr, uint32_t link) {
     const uint32_t first = link & 0x00ffffffu;
     const float4 mn = sc.item_a(first - 1u), mx = sc.item_b(first - 1u);
     float start;
     if (slab_test(mn, mx, tr.fo, trav_exact_inv<true>(tr), tr.best_t, start)) trav_leaf_test(sc, path, tr, link);
 }
-template <class Mem, class Path>
-RT_HD void trav_leaf_step_fast(const SceneT<Mem>& sc, const Path& path, Trav& tr, const TravStack& stk) {  // requires trav_in_leaf(tr)
+template <class Mem, bool kLean, class Path>
+RT_HD void trav_leaf_step_fast(const SceneT<Mem, kLean>& sc, const Path& path, Trav& tr, const TravStack& stk) {  // requires trav_in_leaf(tr)
     trav_leaf_visit_fast(sc, path, tr, tr.cur);
     trav_pop(tr, stk);
 }
 
 // Out-of-line copy of prim_hit_t for rare callers (ConstantMedium boundaries).
 struct TimeOnlyView;
-template <class Mem>
-RT_HD_NOINLINE bool prim_hit_outline(const SceneT<Mem> sc, float4 ia, float4 ib, V3 o, V3 d, float time, uint32_t cur_frame,
+template <class Mem, bool kLean>
+RT_HD_NOINLINE bool prim_hit_outline(const SceneT<Mem, kLean> sc, float4 ia, float4 ib, V3 o, V3 d, float time, uint32_t cur_frame,
                                      uint32_t cur_nops, float t_lo, float t_hi, float& t_out);
 
 struct TimeOnlyView {
@@ -621,8 +628,8 @@ struct TimeOnlyView {
     RT_HD float rtime() const { return time; }
 };
 
-template <class Mem>
-RT_HD_NOINLINE bool prim_hit_outline(const SceneT<Mem> sc, float4 ia, float4 ib, V3 o, V3 d, float time, uint32_t cur_frame,
+template <class Mem, bool kLean>
+RT_HD_NOINLINE bool prim_hit_outline(const SceneT<Mem, kLean> sc, float4 ia, float4 ib, V3 o, V3 d, float time, uint32_t cur_frame,
                                      uint32_t cur_nops, float t_lo, float t_hi, float& t_out) {
     return prim_hit_t(sc, ia, ib, o, d, TimeOnlyView{time}, cur_frame, cur_nops, t_lo, t_hi, t_out);
 }
@@ -632,8 +639,8 @@ struct BestHit {
     float t;
     uint32_t item;
 };
-template <class Mem>
-RT_HD_NOINLINE BestHit medium_hit(const SceneT<Mem> sc, Rng rng, uint32_t bounce, float time, uint32_t i, V3 fo, V3 fd,
+template <class Mem, bool kLean>
+RT_HD_NOINLINE BestHit medium_hit(const SceneT<Mem, kLean> sc, Rng rng, uint32_t bounce, float time, uint32_t i, V3 fo, V3 fd,
                                   uint32_t f_id, uint32_t f_nops, float best_t, uint32_t best) {
     const float4 ia = sc.item_a(i);
     const uint32_t mframe = f2u(ia.w) >> 4;
@@ -672,8 +679,8 @@ RT_HD_NOINLINE BestHit medium_hit(const SceneT<Mem> sc, Rng rng, uint32_t bounce
 // ------------------------------------------------------------------------------------------------
 // Interprets stream items from tr.i until a re-indexed subtree starts (tr.cur = its root) or the
 // stream ends (tr.i = kStreamEnd).
-template <bool kFrames, bool kFast, class Mem, class Path>
-RT_HD void trav_stream(const SceneT<Mem>& sc, const Path& path, Trav& tr) {
+template <bool kFrames, bool kFast, class Mem, bool kLean, class Path>
+RT_HD void trav_stream(const SceneT<Mem, kLean>& sc, const Path& path, Trav& tr) {
     // the last wrapped primitive's frame: the six rects of a rotated prism share one chain
     uint32_t pf_id = tr.f_id;
     V3 po = tr.fo, pd = tr.fd;
@@ -689,7 +696,7 @@ RT_HD void trav_stream(const SceneT<Mem>& sc, const Path& path, Trav& tr) {
         } else if (kind == IT_SPHERE || kind == IT_RECT) {
             const float4 ib = sc.item_b(i);
             const uint32_t frame = f2u(ia.w) >> 4;
-            if (frame != pf_id) {  // (po, pd) = the ray in this primitive's frame; consecutive items mostly share it
+            if (!kLean && frame != pf_id) {  // (po, pd) = the ray in this primitive's frame; consecutive items mostly share it
                 if (frame == tr.f_id) {
                     po = tr.fo;
                     pd = tr.fd;
@@ -711,12 +718,12 @@ RT_HD void trav_stream(const SceneT<Mem>& sc, const Path& path, Trav& tr) {
             const float4 ib = sc.item_b(i);
             float start;
             i = slab_test(ia, ib, tr.fo, trav_exact_inv<kFast>(tr), tr.best_t, start) ? i + 1u : (f2u(ia.w) >> 4);
-        } else if (kind == IT_MEDIUM) {
+        } else if (!kLean && kind == IT_MEDIUM) {
             const BestHit h = medium_hit(sc, path.rng(), path.bounce(), path.rtime(), i, tr.fo, tr.fd, tr.f_id, tr.f_nops, tr.best_t, tr.best);
             tr.best_t = h.t;
             tr.best = h.item;
             i += 2u;
-        } else if (kind == IT_SET_FRAME) {
+        } else if (!kLean && kind == IT_SET_FRAME) {
             if (kFrames) {
                 tr.f_id = f2u(ia.w) >> 4;
                 const uint2 fr = sc.frame(tr.f_id);
@@ -743,8 +750,8 @@ RT_HD void trav_stream(const SceneT<Mem>& sc, const Path& path, Trav& tr) {
 // World::hit_top: the steps above run back to back for one ray.  Returns the index of the winning
 // item (kNoHit if none) and its t.
 // ------------------------------------------------------------------------------------------------
-template <bool kFrames, bool kFast, class Mem>
-RT_HD uint32_t hit_top_stream(const SceneT<Mem>& sc, const PathState& st, float& best_t_out) {
+template <bool kFrames, bool kFast, class Mem, bool kLean>
+RT_HD uint32_t hit_top_stream(const SceneT<Mem, kLean>& sc, const PathState& st, float& best_t_out) {
     Trav tr;
     TravStack stk;
     const PathStateView path{&st};
@@ -771,8 +778,8 @@ RT_HD uint32_t hit_top_stream(const SceneT<Mem>& sc, const PathState& st, float&
 // The body of color()'s loop after hit_top (lib.rs:73-98).  Returns true when the path is finished
 // and `result` holds what color() returns; otherwise st carries the scattered ray.
 // ------------------------------------------------------------------------------------------------
-template <class Mem>
-RT_HD bool shade_and_scatter(const SceneT<Mem>& sc, const KParams& P, PathState& st, uint32_t best, float best_t, V3& result) {
+template <class Mem, bool kLean>
+RT_HD bool shade_and_scatter(const SceneT<Mem, kLean>& sc, const KParams& P, PathState& st, uint32_t best, float best_t, V3& result) {
     result = splat(0.f);
     if (best == kNoHit) {  // lib.rs:100, or the book-1 sky (rtiow_b200.h RTIOW_BG_SKY_GRADIENT)
         if (P.bg_kind == 1u) {
@@ -790,14 +797,14 @@ RT_HD bool shade_and_scatter(const SceneT<Mem>& sc, const KParams& P, PathState&
     uint2 fr;
     fr.x = 0u; fr.y = 0u;
     V3 lo = st.ro, ld = st.rd;
-    if (frame != 0u) {
+    if (!kLean && frame != 0u) {
         fr = sc.frame(frame);
         const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * fr.x, fr.y, lo, ld, st.rtime);
         lo = r.o;
         ld = r.d;
     }
     V3 p, n;
-    if (kind == IT_SPHERE) {
+    if (kLean || kind == IT_SPHERE) {
         if (flags & FL_HAS_OFFSET) lo = lo - mk(ib.x, ib.y, ib.z);
         p = lo + best_t * ld;  // ray.point_at_parameter(t)  object.rs:100
         n = p / ia.x;          // object.rs:104
@@ -812,7 +819,7 @@ RT_HD bool shade_and_scatter(const SceneT<Mem>& sc, const KParams& P, PathState&
         p = lo + best_t * ld;
         n = mk(1.f, 0.f, 0.f);
     }
-    if (fr.y != 0u) {
+    if (!kLean && fr.y != 0u) {
         const Ray6 r = frame_ops_hit(sc.m, sc.off_ops + 16u * fr.x, fr.y, p, n);
         p = r.o;
         n = r.d;
@@ -823,7 +830,7 @@ RT_HD bool shade_and_scatter(const SceneT<Mem>& sc, const KParams& P, PathState&
     const uint32_t mkind = f2u(m0.x) & 0xffu;
     const V3 rd = st.rd;
     bool done = false;
-    if (mkind == MAT_DIFFUSE_LIGHT) {
+    if (!kLean && mkind == MAT_DIFFUSE_LIGHT) {
         // accum = accum + strength * (brightness * emission(p)); no scatter -> return accum  (lib.rs:76,88-91)
         result = splat(0.f) + st.strength * (m0.z * material_texture(sc, m0, m1, p));
         return true;
@@ -852,7 +859,7 @@ RT_HD bool shade_and_scatter(const SceneT<Mem>& sc, const KParams& P, PathState&
         st.ro = p;
         if (dot(st.rd, n) > 0.f) st.strength = st.strength * mk(m1.x, m1.y, m1.z);
         else done = true;                      // absorbed: return accum (= 0)
-    } else if (mkind == MAT_DIELECTRIC) {      // material.rs:82-107
+    } else if (kLean || mkind == MAT_DIELECTRIC) {  // material.rs:82-107
         const float ref_idx = m0.z;
         V3 outward_normal;
         float ni_over_nt, cosine;

@@ -57,7 +57,7 @@ __device__ __forceinline__ void stage_scene_tma(unsigned char* smem_dst, const u
     }
 }
 
-template <bool kSmem, bool kFrames, bool kFast, int kThreads, int kMinBlocks>
+template <bool kSmem, bool kFrames, bool kFast, bool kLean, int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __grid_constant__ KParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
     } else {
         mem.base = P.blob;
     }
-    const SceneT<Mem> sc = scene_views(mem, P);
+    const SceneT<Mem, kLean> sc = scene_views<kLean>(mem, P);
 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -136,8 +136,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
             active = true;
         }
         const bool warp_alive = __ballot_sync(0xffffffffu, active) != 0u;
+        // Phase barriers exist only in the kernels for scenes with wrapper frames on subtrees (kFrames): those are
+        // the ones whose code outgrows the instruction cache (rtiow_b200.cu, phase_sync).
         const uint32_t bar_id = 1u + (threadIdx.x >> 5) / P.phase_group, bar_threads = P.phase_group * 32u;
-        if (P.phase_sync != 0u) {
+        if (kFrames && P.phase_sync != 0u) {
             // the warps of a barrier group enter hit_top together (and leave the kernel together): their
             // instruction fetches then hit the same few KB of code instead of the whole kernel
             uint32_t any;
@@ -154,12 +156,26 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
             break;
         }
 
-        // ============ 2. World::hit_top ============================================================
-        float best_t = 0.f;
-        uint32_t best = kNoHit;
-        if (active) best = hit_top_stream<kFrames, kFast>(sc, st, best_t);
-        if (P.phase_sync == 2u) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
-        if (active) {
+        if (kFrames) {
+            // ============ 2. World::hit_top ========================================================
+            float best_t = 0.f;
+            uint32_t best = kNoHit;
+            if (active) best = hit_top_stream<kFrames, kFast>(sc, st, best_t);
+            if (P.phase_sync == 2u) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
+            // ============ 3. emitted + scatter =====================================================
+            if (active) {
+                const uint32_t segs = st.bounce + 1u;
+                V3 result;
+                if (shade_and_scatter(sc, P, st, best, best_t, result)) {
+                    P.staging[static_cast<size_t>(st.samp - P.s_begin) * P.npix + st.pix] =
+                        make_float4(result.x, result.y, result.z, static_cast<float>(segs));
+                    active = false;
+                }
+            }
+        } else if (active) {
+            // ============ 2. World::hit_top ========================================================
+            float best_t;
+            const uint32_t best = hit_top_stream<kFrames, kFast>(sc, st, best_t);
             // ============ 3. emitted + scatter =====================================================
             const uint32_t segs = st.bounce + 1u;
             V3 result;

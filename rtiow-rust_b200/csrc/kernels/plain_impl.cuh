@@ -4,19 +4,21 @@
 
 namespace rtiow {
 namespace {
-template <bool F, bool Q>
+template <bool F, bool Q, bool L>
 KernelVariant by_threads(uint32_t threads) {
     switch (threads) {
-        case 256: return {render_kernel<RTIOW_PLAIN_SMEM, F, Q, 256, 1>, 256};
-        case 512: return {render_kernel<RTIOW_PLAIN_SMEM, F, Q, 512, 1>, 512};
-        case 768: return {render_kernel<RTIOW_PLAIN_SMEM, F, Q, 768, 1>, 768};
+        case 256: return {render_kernel<RTIOW_PLAIN_SMEM, F, Q, L, 256, 1>, 256};
+        case 512: return {render_kernel<RTIOW_PLAIN_SMEM, F, Q, L, 512, 1>, 512};
+        case 768: return {render_kernel<RTIOW_PLAIN_SMEM, F, Q, L, 768, 1>, 768};
         default: return {nullptr, 0};
     }
 }
 }  // namespace
 
-KernelVariant RTIOW_PLAIN_NAME(bool frames, bool fast, uint32_t threads) {
-    if (frames) return fast ? by_threads<true, true>(threads) : by_threads<true, false>(threads);
-    return fast ? by_threads<false, true>(threads) : by_threads<false, false>(threads);
+// lean: the spheres-only specialisation (path_logic.cuh SceneT); never combined with frames
+KernelVariant RTIOW_PLAIN_NAME(bool frames, bool fast, bool lean, uint32_t threads) {
+    if (lean && !frames) return fast ? by_threads<false, true, true>(threads) : by_threads<false, false, true>(threads);
+    if (frames) return fast ? by_threads<true, true, false>(threads) : by_threads<true, false, false>(threads);
+    return fast ? by_threads<false, true, false>(threads) : by_threads<false, false, false>(threads);
 }
 }  // namespace rtiow

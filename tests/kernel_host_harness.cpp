@@ -15,9 +15,10 @@
 // accel = 1: the re-indexed (SAH, ordered) traversal with conservative inner box tests that the device
 // uses by default; 2: the same tree with the reference's exact box test at every node; 0: the plain
 // reference-order stream.
-extern "C" __attribute__((visibility("default"))) int harness_render(const rtiow_scene_desc_t* desc, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny,
-                              uint32_t ns, uint64_t seed, uint32_t row_begin, uint32_t row_end, float* out_rgb,
-                              float* out_samples, int accel, uint32_t* layout_out, uint32_t row_step, uint32_t row_band) {
+template <bool kLean>
+static int harness_render_impl(const rtiow_scene_desc_t* desc, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny,
+                               uint32_t ns, uint64_t seed, uint32_t row_begin, uint32_t row_end, float* out_rgb,
+                               float* out_samples, int accel, uint32_t* layout_out, uint32_t row_step, uint32_t row_band) {
     using namespace rtiow;
     bool has_frames = false, uses_perlin = false;
     std::string msg;
@@ -43,7 +44,7 @@ extern "C" __attribute__((visibility("default"))) int harness_render(const rtiow
     P.bg_kind = desc->background_kind;
     std::memcpy(P.bg0, desc->background_c0, 12);
     std::memcpy(P.bg1, desc->background_c1, 12);
-    const SceneT<MemPtr> sc = scene_views(MemPtr{blob.data()}, P);
+    const SceneT<MemPtr, kLean> sc = scene_views<kLean>(MemPtr{blob.data()}, P);
     for (uint32_t pix = 0; pix < P.npix; ++pix) {
         float acc[3] = {0.f, 0.f, 0.f};
         for (uint32_t s = 0; s < ns; ++s) {
@@ -74,6 +75,18 @@ extern "C" __attribute__((visibility("default"))) int harness_render(const rtiow
     return 0;
 }
 
+// accel: low byte as above; bit 8 asks for the spheres-only specialisation of the per-path code (ignored, like in
+// the library, when the scene does not qualify).
+extern "C" __attribute__((visibility("default"))) int harness_render(const rtiow_scene_desc_t* desc, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny,
+                              uint32_t ns, uint64_t seed, uint32_t row_begin, uint32_t row_end, float* out_rgb,
+                              float* out_samples, int accel, uint32_t* layout_out, uint32_t row_step, uint32_t row_band) {
+    const bool lean = (accel & 0x100) != 0 && rtiow::lean_scene(desc);
+    accel &= 0xff;
+    if (layout_out) layout_out[4] = lean ? 1u : 0u;
+    return lean ? harness_render_impl<true>(desc, cam, nx, ny, ns, seed, row_begin, row_end, out_rgb, out_samples, accel, layout_out, row_step, row_band)
+                : harness_render_impl<false>(desc, cam, nx, ny, ns, seed, row_begin, row_end, out_rgb, out_samples, accel, layout_out, row_step, row_band);
+}
+
 // hit_top for caller-supplied rays: n rays as {ox, oy, oz, dx, dy, dz, time}; out[2*i] = winning item of the
 // REFERENCE-ORDER stream (0xffffffff = none, comparable across traversal modes through its primitive record),
 // out[2*i+1] = bits of t.  Used to pit the three traversals against each other on adversarial rays.
@@ -89,7 +102,7 @@ extern "C" __attribute__((visibility("default"))) int harness_trace_rays(const r
     P.blob = blob.data();
     P.off_nodes = lay.off_nodes; P.off_frames = lay.off_frames; P.off_ops = lay.off_ops; P.off_mats = lay.off_mats; P.off_tex = lay.off_tex;
     P.off_pvecs = lay.off_pvecs; P.off_pperm = lay.off_pperm; P.off_fnodes = lay.off_fnodes;
-    const SceneT<MemPtr> sc = scene_views(MemPtr{blob.data()}, P);
+    const SceneT<MemPtr, false> sc = scene_views<false>(MemPtr{blob.data()}, P);
     const bool fast = accel == 1;
     for (uint32_t i = 0; i < n; ++i) {
         PathState st;

@@ -198,7 +198,7 @@ def test_reindexed_subtrees_layout():
     on the reference-order stream."""
     def layout(name, bvh, accel=2):
         world, cam = R.build_scene(name, 8, 8, use_bvh=bvh)
-        lay = np.zeros(4, np.uint32)
+        lay = np.zeros(5, np.uint32)
         H.render(world, cam, 8, 8, 1, accel=accel, layout=lay)
         return world.counts(), dict(items=int(lay[0]), nodes=int(lay[1]), accels=int(lay[2]), depth=int(lay[3]))
     c, l = layout("book1", True)
@@ -303,3 +303,21 @@ def test_conservative_box_test_error_bound():
             worst = max(worst, float((np.abs(ref.astype(np.float64) - fast.astype(np.float64))[ok] / unit[ok]).max()))
     assert worst <= 4.0, worst      # the analytic bound
     assert worst * 4 <= 16.0        # the kernel's slack per side leaves a factor of 4
+
+
+def test_spheres_only_specialisation_matches_the_general_code(oracle):
+    """The lean instantiation of the per-path code (SceneT<Mem, true>: rects, wrapper chains, media, lights and
+    procedural textures compiled out) is picked for book-1 only and gives the same bits as the general one."""
+    nx, ny, ns = 48, 32, 6
+    for name, bvh, qualifies in (("book1", True, True), ("book1", False, True), ("kitchen_sink", True, False), ("cornell", False, False)):
+        world, cam = R.build_scene(name, nx, ny, use_bvh=bvh)
+        lay = np.zeros(5, np.uint32)
+        general, gs = H.render(world, cam, nx, ny, ns, want_samples=True, accel=1)
+        lean, ls = H.render(world, cam, nx, ny, ns, want_samples=True, accel=1, lean=True, layout=lay)
+        assert bool(lay[4]) == qualifies, name
+        assert np.array_equal(general.view(np.uint32), lean.view(np.uint32)) and np.array_equal(gs.view(np.uint32), ls.view(np.uint32))
+    want, _, _ = oracle.Scene("book1", nx, ny).render(ns, nthreads=os.cpu_count() or 4)
+    world, cam = R.build_scene("book1", nx, ny, use_bvh=True)
+    for accel in (1, 2, 0):
+        got, _ = H.render(world, cam, nx, ny, ns, accel=accel, lean=True)
+        assert n_diff(got, want) == 0, accel
