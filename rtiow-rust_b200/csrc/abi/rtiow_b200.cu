@@ -324,9 +324,10 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     if (int rc = ensure_uploaded(s, B)) return rc;
     const bool fast = mode == rtiow::kBlobFast && B.lay.n_nodes != 0;
     const bool smem = B.bytes <= smem_cap && !s->force_global;
-    // 0 = automatic: 768 threads (80 registers) per CTA, one CTA per SM
-    const uint32_t threads = s->cta_threads ? s->cta_threads : 768u;
+    // 0 = automatic: one CTA per SM; 768 threads (80 registers) for the general kernel, 1024 (64 registers) for the
+    // spheres-only one, which needs no more
     const bool lean = s->lean_scene && s->specialise;
+    const uint32_t threads = s->cta_threads ? s->cta_threads : (lean ? 1024u : 768u);
     const KernelVariant var = smem ? rtiow::pick_plain_smem(s->has_frames, fast, lean, threads)
                                    : rtiow::pick_plain_global(s->has_frames, fast, lean, threads);
     if (!var.fn) return set_err(RTIOW_ERR_INVALID_ARG, "no kernel instantiation for this cta_threads");
@@ -340,7 +341,9 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     const uint32_t n_groups = tiles_x * ((n_rows + rtiow::kTileH - 1u) / rtiow::kTileH);  // 8x4-pixel tiles
     uint32_t grid = static_cast<uint32_t>(s->sm_count) * static_cast<uint32_t>(occ);
     const uint32_t warps_per_cta = static_cast<uint32_t>(var.threads) / 32u;
-    grid = std::max(1u, std::min(grid, (n_groups + warps_per_cta - 1) / warps_per_cta));
+    // no more CTAs than there is work for: a warp takes at least one unit (one sample of one tile)
+    const uint64_t min_units = static_cast<uint64_t>(n_groups) * std::min(s_pass, ns);
+    grid = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(grid, (min_units + warps_per_cta - 1) / warps_per_cta)));
     cudaFuncAttributes fa{};
     CK(cudaFuncGetAttributes(&fa, var.fn));
 
@@ -541,8 +544,8 @@ void rtiow_b200_scene_destroy(rtiow_scene_t* s) {
 int rtiow_b200_set_tuning(rtiow_scene_t* s, uint32_t cta_threads, uint32_t ctas_per_sm, uint32_t staging_mib, int force_global) {
     if (!s) return set_err(RTIOW_ERR_INVALID_ARG, "null scene");
     if (cta_threads) {
-        if (cta_threads != 256 && cta_threads != 512 && cta_threads != 768)
-            return set_err(RTIOW_ERR_INVALID_ARG, "cta_threads must be 256, 512 or 768");
+        if (cta_threads != 256 && cta_threads != 512 && cta_threads != 768 && cta_threads != 1024)
+            return set_err(RTIOW_ERR_INVALID_ARG, "cta_threads must be 256, 512, 768 or (spheres-only kernel) 1024");
     }
     s->cta_threads = cta_threads;
     s->ctas_per_sm = ctas_per_sm;

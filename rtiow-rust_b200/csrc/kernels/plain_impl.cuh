@@ -10,6 +10,7 @@ KernelVariant by_threads(uint32_t threads) {
         case 256: return {render_kernel<RTIOW_PLAIN_SMEM, F, Q, L, 256, 1>, 256};
         case 512: return {render_kernel<RTIOW_PLAIN_SMEM, F, Q, L, 512, 1>, 512};
         case 768: return {render_kernel<RTIOW_PLAIN_SMEM, F, Q, L, 768, 1>, 768};
+        case 1024: if (L) return {render_kernel<RTIOW_PLAIN_SMEM, F, Q, true, 1024, 1>, 1024}; return {nullptr, 0};
         default: return {nullptr, 0};
     }
 }
