@@ -179,7 +179,8 @@ typedef struct rtiow_stats_t {
     uint32_t accel_nodes;    /* nodes of the library's own index over the scene's Bvh subtrees (0 = none) */
     uint32_t accel_subtrees; /* how many Bvh subtrees were re-indexed                                      */
     uint32_t traversal;      /* RTIOW_TRAVERSAL_*: how the last render walked Bvh subtrees                 */
-    uint32_t lean_kernel;    /* 1 if the last render used the spheres-only specialisation of the megakernel */
+    uint32_t kernel_profile; /* which compilation of the megakernel the last render used: 0 general, 1 spheres-only
+                                scenes, 2 rect-list scenes (rtiow_b200_set_specialisation)                  */
 } rtiow_stats_t;
 
 typedef struct rtiow_scene rtiow_scene_t;
@@ -239,10 +240,11 @@ RTIOW_API int rtiow_b200_get_stats(rtiow_scene_t* scene, rtiow_stats_t* out);
 RTIOW_API int rtiow_b200_set_tuning(rtiow_scene_t* scene, uint32_t cta_threads, uint32_t ctas_per_sm, uint32_t staging_mib,
                           int force_global);
 
-/* The megakernel is compiled twice: for any scene, and for scenes that hold nothing but unwrapped spheres with
- * Lambertian / Metal / Dielectric materials and constant textures (book-1's random_scene) — the same per-path
- * code with everything else compiled out: half the instructions, no register spills.  Picked automatically
- * from the scene's content; enable = 0 forces the general kernel.  Same image either way. */
+/* The megakernel is compiled for three feature sets: any scene; scenes that hold nothing but unwrapped spheres
+ * with Lambertian / Metal / Dielectric materials and constant textures (book-1's random_scene); and lists of
+ * rects, wrapped or not, with Lambertian and DiffuseLight materials (the Cornell box) — the same per-path code
+ * with everything else compiled out: half the instructions, no register spills.  Picked automatically from the
+ * scene's content; enable = 0 forces the general kernel.  Same image either way. */
 RTIOW_API int rtiow_b200_set_specialisation(rtiow_scene_t* scene, int enable);
 
 /* How `Bvh` subtrees (src/bvh.rs) are walked.  All give the same image bit for bit; the choice is

@@ -60,7 +60,7 @@ class Stats(C.Structure):
                 ("segments", C.c_uint64), ("kernel_launches", C.c_uint32), ("passes", C.c_uint32),
                 ("scene_in_smem", C.c_uint32), ("scene_bytes", C.c_uint32), ("grid", C.c_uint32),
                 ("block", C.c_uint32), ("dyn_smem_bytes", C.c_uint32), ("regs_per_thread", C.c_uint32),
-                ("accel_nodes", C.c_uint32), ("accel_subtrees", C.c_uint32), ("traversal", C.c_uint32), ("lean_kernel", C.c_uint32)]
+                ("accel_nodes", C.c_uint32), ("accel_subtrees", C.c_uint32), ("traversal", C.c_uint32), ("kernel_profile", C.c_uint32)]
 
 
 # every symbol include/rtiow_b200.h declares

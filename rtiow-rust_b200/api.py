@@ -138,7 +138,7 @@ class World:
         _check(N.abi().rtiow_b200_set_tuning(self.gpu(device), cta_threads, ctas_per_sm, staging_mib, int(force_global)))
 
     def set_specialisation(self, enable=True, device=0):
-        """False forces the general megakernel even if the scene qualifies for the spheres-only one.  Same image."""
+        """False forces the general megakernel even if the scene qualifies for a specialised one.  Same image."""
         _check(N.abi().rtiow_b200_set_specialisation(self.gpu(device), int(bool(enable))))
 
     def set_traversal(self, mode, device=0):

@@ -15,7 +15,8 @@ struct KernelVariant {
 };
 
 // render_kernel (render_kernel.cuh): one path per lane.  threads in {256, 512, 768}.
-KernelVariant pick_plain_smem(bool frames, bool fast, bool lean, uint32_t threads);
-KernelVariant pick_plain_global(bool frames, bool fast, bool lean, uint32_t threads);
+// profile: 0 general, 1 spheres-only (path_logic.cuh kFeatSpheres), 2 rect lists (kFeatRects); threads 1024 for 1 and 2 only
+KernelVariant pick_plain_smem(bool frames, bool fast, uint32_t profile, uint32_t threads);
+KernelVariant pick_plain_global(bool frames, bool fast, uint32_t profile, uint32_t threads);
 
 }  // namespace rtiow

@@ -239,8 +239,8 @@ struct rtiow_scene {
     // tuning
     uint32_t cta_threads = 0, ctas_per_sm = 0, staging_mib = 2048, sample_chunk = 0;
     bool force_global = false;
-    bool lean_scene = false;       // only world-frame spheres, Lambertian / Metal / Dielectric, constant textures
-    bool specialise = true;        // use the lean kernel for lean scenes (same image, fewer instructions)
+    uint32_t features = 0;         // scene_blob.hpp scene_features()
+    bool specialise = true;        // use a kernel compiled for a subset of features when the scene allows (same image)
     uint32_t refill_lanes = 0;     // 0 = automatic
     bool costly_segments = false;  // the scene has wrapper frames on subtrees or constant media
 
@@ -326,10 +326,16 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     const bool smem = B.bytes <= smem_cap && !s->force_global;
     // 0 = automatic: one CTA per SM; 768 threads (80 registers) for the general kernel, 1024 (64 registers) for the
     // spheres-only one, which needs no more
-    const bool lean = s->lean_scene && s->specialise;
-    const uint32_t threads = s->cta_threads ? s->cta_threads : (lean ? 1024u : 768u);
-    const KernelVariant var = smem ? rtiow::pick_plain_smem(s->has_frames, fast, lean, threads)
-                                   : rtiow::pick_plain_global(s->has_frames, fast, lean, threads);
+    // kernel profile: the smallest compiled feature mask that covers the scene (the re-indexed subtrees add SF_ACCEL)
+    const uint32_t needs = s->features | (B.lay.n_accel ? static_cast<uint32_t>(rtiow::SF_ACCEL) : 0u);
+    uint32_t profile = 0;
+    if (s->specialise && !s->has_frames) {
+        if ((needs & ~rtiow::kFeatSpheres) == 0u) profile = 1;
+        else if ((needs & ~rtiow::kFeatRects) == 0u) profile = 2;
+    }
+    const uint32_t threads = s->cta_threads ? s->cta_threads : (profile ? 1024u : 768u);
+    const KernelVariant var = smem ? rtiow::pick_plain_smem(s->has_frames, fast, profile, threads)
+                                   : rtiow::pick_plain_global(s->has_frames, fast, profile, threads);
     if (!var.fn) return set_err(RTIOW_ERR_INVALID_ARG, "no kernel instantiation for this cta_threads");
     const size_t dyn_smem = smem ? B.bytes : 0;
     CK(cudaFuncSetAttribute(var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem)));
@@ -438,7 +444,7 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     s->stats.block = static_cast<uint32_t>(var.threads);
     s->stats.dyn_smem_bytes = static_cast<uint32_t>(dyn_smem);
     s->stats.regs_per_thread = static_cast<uint32_t>(fa.numRegs);
-    s->stats.lean_kernel = lean ? 1u : 0u;
+    s->stats.kernel_profile = profile;
     s->stats.traversal = static_cast<uint32_t>(mode == rtiow::kBlobFast ? RTIOW_TRAVERSAL_REINDEXED
                                                : (mode == rtiow::kBlobExact ? RTIOW_TRAVERSAL_REINDEXED_EXACT : RTIOW_TRAVERSAL_REFERENCE_ORDER));
     return RTIOW_OK;
@@ -488,7 +494,7 @@ int rtiow_b200_scene_create(const rtiow_scene_desc_t* d, int device, rtiow_scene
     s->has_frames = has_frames;
     s->costly_segments = has_frames;
     for (uint32_t i = 0; i < d->n_items; ++i) s->costly_segments |= (d->items[i].a_w & 15u) == RTIOW_ITEM_MEDIUM;
-    s->lean_scene = rtiow::lean_scene(d);
+    s->features = rtiow::scene_features(d);
     s->bg_kind = d->background_kind;
     std::memcpy(s->bg0, d->background_c0, 12);
     std::memcpy(s->bg1, d->background_c1, 12);
@@ -545,7 +551,7 @@ int rtiow_b200_set_tuning(rtiow_scene_t* s, uint32_t cta_threads, uint32_t ctas_
     if (!s) return set_err(RTIOW_ERR_INVALID_ARG, "null scene");
     if (cta_threads) {
         if (cta_threads != 256 && cta_threads != 512 && cta_threads != 768 && cta_threads != 1024)
-            return set_err(RTIOW_ERR_INVALID_ARG, "cta_threads must be 256, 512, 768 or (spheres-only kernel) 1024");
+            return set_err(RTIOW_ERR_INVALID_ARG, "cta_threads must be 256, 512, 768 or (specialised kernels) 1024");
     }
     s->cta_threads = cta_threads;
     s->ctas_per_sm = ctas_per_sm;

@@ -125,23 +125,26 @@ inline int validate_desc(const rtiow_scene_desc_t* d, bool* has_frames, bool* us
 // How Bvh subtrees are laid out for the device (rtiow_b200.h RTIOW_TRAVERSAL_*).
 enum BlobMode { kBlobFast = 0, kBlobReferenceOrder = 1, kBlobExact = 2 };
 
-// Can the spheres-only kernel specialisation render this scene?  (path_logic.cuh SceneT<Mem, kLean>)
-inline bool lean_scene(const rtiow_scene_desc_t* d) {
+// The features of a scene (path_logic.cuh SF_*), without SF_ACCEL (that depends on how the blob is built).
+inline uint32_t scene_features(const rtiow_scene_desc_t* d) {
+    uint32_t f = 0;
+    auto wrapped = [&](uint32_t frame) { return frame < d->n_frames && d->frames[frame].n_ops != 0; };
     for (uint32_t i = 0; i < d->n_items; ++i) {
         const uint32_t kind = d->items[i].a_w & 15u, payload = d->items[i].a_w >> 4;
-        if (kind == RTIOW_ITEM_SPHERE) {
-            if (payload != 0) return false;                                  // a wrapper chain
-            if (((d->items[i].b_w >> 24) & RTIOW_FLAG_FLIP) != 0) return false;
-        } else if (kind != RTIOW_ITEM_BBOX && kind != RTIOW_ITEM_END) {
-            return false;                                                        // rects, media, frame switches
-        }
+        if (kind == RTIOW_ITEM_SPHERE) f |= 1u | (wrapped(payload) ? 4u : 0u);
+        else if (kind == RTIOW_ITEM_RECT) f |= 2u | (wrapped(payload) ? 4u : 0u);
+        else if (kind == RTIOW_ITEM_MEDIUM) f |= 8u | (wrapped(payload) ? 4u : 0u);
+        else if (kind == RTIOW_ITEM_SET_FRAME) f |= 4u;
     }
     for (uint32_t m = 0; m < d->n_materials; ++m) {
         const rtiow_material_t& mt = d->materials[m];
-        if (mt.kind > RTIOW_MAT_DIELECTRIC) return false;                        // lights, Isotropic
-        if (mt.kind == RTIOW_MAT_LAMBERTIAN && d->textures[mt.tex].kind != RTIOW_TEX_CONSTANT) return false;
+        const bool textured = mt.kind == RTIOW_MAT_LAMBERTIAN || mt.kind == RTIOW_MAT_DIFFUSE_LIGHT || mt.kind == RTIOW_MAT_ISOTROPIC;
+        if (textured && d->textures[mt.tex].kind != RTIOW_TEX_CONSTANT) f |= 16u;
+        if (mt.kind == RTIOW_MAT_DIFFUSE_LIGHT) f |= 32u;
+        if (mt.kind == RTIOW_MAT_ISOTROPIC) f |= 64u;
+        if (mt.kind == RTIOW_MAT_METAL || mt.kind == RTIOW_MAT_DIELECTRIC) f |= 128u;
     }
-    return true;
+    return f;
 }
 
 struct BlobLayout {

@@ -90,12 +90,30 @@ struct MemGlobal {
 };
 #endif
 
-// Views into the scene blob.  kLean: the scene holds nothing but world-frame spheres with Lambertian / Metal /
-// Dielectric materials and constant textures (rtiow_b200.cu lean_scene()), so rects, wrapper chains, media,
-// lights, Isotropic and procedural textures compile out of the megakernel: half the code, no register spills.
-template <class Mem, bool kLean = false>
+// What a scene can contain.  The megakernel is compiled for a few feature masks (csrc/kernels): a kernel built
+// for mask M renders every scene whose features are a subset of M, and everything outside M compiles out of it —
+// book-1's random_scene (unwrapped spheres, Lambertian / Metal / Dielectric, one re-indexed Bvh) needs 1.8 k
+// SASS instructions instead of 4.2 k and no register spills; the Cornell box (rects, two rotated prisms, a
+// light) needs no traversal stack at all.  scene_blob.hpp scene_features() computes a scene's mask.
+enum : uint32_t {
+    SF_SPHERE = 1u,      // Sphere items
+    SF_RECT = 2u,        // Rect items
+    SF_WRAP = 4u,        // a primitive or medium under a wrapper chain (Translate / Scale / RotateY / LinearMove / Flip op)
+    SF_MEDIUM = 8u,      // ConstantMedium
+    SF_TEXTURE = 16u,    // checker / Perlin textures
+    SF_LIGHT = 32u,      // DiffuseLight
+    SF_ISOTROPIC = 64u,  // Isotropic
+    SF_SPECULAR = 128u,  // Metal, Dielectric
+    SF_ACCEL = 256u,     // re-indexed Bvh subtrees (node / leaf traversal with a per-lane stack)
+    SF_ALL = 511u
+};
+constexpr uint32_t kFeatSpheres = SF_SPHERE | SF_SPECULAR | SF_ACCEL;  // book-1
+constexpr uint32_t kFeatRects = SF_RECT | SF_WRAP | SF_LIGHT;          // Cornell box
+
+// Views into the scene blob.
+template <class Mem, uint32_t kFeat = SF_ALL>
 struct SceneT {
-    static constexpr bool lean = kLean;
+    static constexpr uint32_t feat = kFeat;
     Mem m;
     uint32_t off_nodes, off_frames, off_ops, off_mats, off_tex, off_pvecs, off_pperm, off_fnodes;
     RT_HD float4 item_a(uint32_t i) const { return m.ld4(32u * i); }
@@ -109,9 +127,9 @@ struct SceneT {
     RT_HD uint32_t pperm(uint32_t i) const { return m.ld1b(off_pperm + i); }
 };
 
-template <bool kLean, class Mem>
-RT_HD SceneT<Mem, kLean> scene_views(Mem m, const KParams& P) {
-    SceneT<Mem, kLean> sc;
+template <uint32_t kFeat, class Mem>
+RT_HD SceneT<Mem, kFeat> scene_views(Mem m, const KParams& P) {
+    SceneT<Mem, kFeat> sc;
     sc.m = m;
     sc.off_nodes = P.off_nodes; sc.off_frames = P.off_frames; sc.off_ops = P.off_ops; sc.off_mats = P.off_mats;
     sc.off_tex = P.off_tex; sc.off_pvecs = P.off_pvecs; sc.off_pperm = P.off_pperm;
@@ -247,34 +265,33 @@ RT_HD bool rect_hit_t(V3 o, V3 d, uint32_t axis, float4 ia, float4 ib, float t_l
 // Any primitive item against a ray (o, d) that is already in frame `cur_frame` (whose chain has
 // `cur_nops` ops, a prefix of the item's own chain): the item's remaining wrappers are applied
 // first, exactly like the nested Object::hit calls.
-template <class Mem, bool kLean, class Path>
-RT_HD bool prim_hit_t(const SceneT<Mem, kLean>& sc, float4 ia, float4 ib, V3 o, V3 d, const Path& path, uint32_t cur_frame,
+template <class Mem, uint32_t kFeat, class Path>
+RT_HD bool prim_hit_t(const SceneT<Mem, kFeat>& sc, float4 ia, float4 ib, V3 o, V3 d, const Path& path, uint32_t cur_frame,
                       uint32_t cur_nops, float t_lo, float t_hi, float& t_out) {
     const uint32_t kind = f2u(ia.w) & 15u;
     const uint32_t frame = f2u(ia.w) >> 4;
     const uint32_t flags = f2u(ib.w) >> 24;
-    if (kLean) {  // a world-frame sphere, nothing else exists in the scene
+    if (kFeat & SF_WRAP) {
+        if (frame != cur_frame) {
+            const uint2 fr = sc.frame(frame);
+            const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * (fr.x + cur_nops), fr.y - cur_nops, o, d, path.rtime());
+            o = r.o;
+            d = r.d;
+        }
+    }
+    if ((kFeat & SF_SPHERE) && (!(kFeat & SF_RECT) || kind == IT_SPHERE)) {
         if (flags & FL_HAS_OFFSET) o = o - mk(ib.x, ib.y, ib.z);
         return sphere_hit_t(o, d, ia.x, t_lo, t_hi, t_out);
     }
-    if (frame != cur_frame) {
-        const uint2 fr = sc.frame(frame);
-        const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * (fr.x + cur_nops), fr.y - cur_nops, o, d, path.rtime());
-        o = r.o;
-        d = r.d;
-    }
-    if (kind == IT_SPHERE) {
-        if (flags & FL_HAS_OFFSET) o = o - mk(ib.x, ib.y, ib.z);
-        return sphere_hit_t(o, d, ia.x, t_lo, t_hi, t_out);
-    }
-    return rect_hit_t(o, d, (flags >> 2) & 3u, ia, ib, t_lo, t_hi, t_out);
+    if (kFeat & SF_RECT) return rect_hit_t(o, d, (flags >> 2) & 3u, ia, ib, t_lo, t_hi, t_out);
+    return false;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Textures (texture.rs) and Perlin noise (perlin.rs)
 // ------------------------------------------------------------------------------------------------
-template <class Mem, bool kLean>
-RT_HD_NOINLINE float perlin_noise(const SceneT<Mem, kLean>& sc, V3 p) {  // perlin.rs:49-64 + trilinear_interp :31-47
+template <class Mem, uint32_t kFeat>
+RT_HD_NOINLINE float perlin_noise(const SceneT<Mem, kFeat>& sc, V3 p) {  // perlin.rs:49-64 + trilinear_interp :31-47
     const V3 ijk = mk(floorf(p.x), floorf(p.y), floorf(p.z));
     const V3 uvw = p - ijk;
     const int bi = f2i_rz_sat(ijk.x), bj = f2i_rz_sat(ijk.y), bk = f2i_rz_sat(ijk.z);  // `as i32`
@@ -299,8 +316,8 @@ RT_HD_NOINLINE float perlin_noise(const SceneT<Mem, kLean>& sc, V3 p) {  // perl
     return accum;
 }
 
-template <class Mem, bool kLean>
-RT_HD_NOINLINE float perlin_turb(const SceneT<Mem, kLean>& sc, V3 p) {  // perlin.rs:66-75 with depth 7 (texture.rs:24)
+template <class Mem, uint32_t kFeat>
+RT_HD_NOINLINE float perlin_turb(const SceneT<Mem, kFeat>& sc, V3 p) {  // perlin.rs:66-75 with depth 7 (texture.rs:24)
     float accum = 0.f, weight = 1.f;
     for (int i = 0; i < 7; ++i) {
         accum += weight * perlin_noise(sc, p);
@@ -310,8 +327,8 @@ RT_HD_NOINLINE float perlin_turb(const SceneT<Mem, kLean>& sc, V3 p) {  // perli
     return fabsf(accum);
 }
 
-template <class Mem, bool kLean>
-RT_HD_NOINLINE V3 texture_eval(const SceneT<Mem, kLean>& sc, uint32_t id, V3 p) {
+template <class Mem, uint32_t kFeat>
+RT_HD_NOINLINE V3 texture_eval(const SceneT<Mem, kFeat>& sc, uint32_t id, V3 p) {
     for (;;) {
         const float4 t0 = sc.tex(id, 0u);
         const uint32_t kind = f2u(t0.x);
@@ -325,10 +342,10 @@ RT_HD_NOINLINE V3 texture_eval(const SceneT<Mem, kLean>& sc, uint32_t id, V3 p) 
 }
 
 // Material's texture at p; constant textures were baked into the material record at scene upload.
-template <class Mem, bool kLean>
-RT_HD V3 material_texture(const SceneT<Mem, kLean>& sc, float4 m0, float4 m1, V3 p) {
+template <class Mem, uint32_t kFeat>
+RT_HD V3 material_texture(const SceneT<Mem, kFeat>& sc, float4 m0, float4 m1, V3 p) {
     const uint32_t texkind = (f2u(m0.x) >> 8) & 0xffu;
-    if (kLean || texkind == TEX_CONSTANT) return mk(m1.x, m1.y, m1.z);
+    if (!(kFeat & SF_TEXTURE) || texkind == TEX_CONSTANT) return mk(m1.x, m1.y, m1.z);
     return texture_eval(sc, f2u(m0.y), p);
 }
 
@@ -476,8 +493,8 @@ RT_HD void trav_pop(Trav& tr, const TravStack& stk) {
 // smallest t, and among equal t the item that comes first in the reference's visiting order, which
 // is what `t < t_range.end` with a shrinking end gives in Bvh::hit (bvh.rs:94-106).
 // ------------------------------------------------------------------------------------------------
-template <class Mem, bool kLean>
-RT_HD void trav_node_step(const SceneT<Mem, kLean>& sc, Trav& tr, TravStack& stk) {  // requires trav_in_node(tr)
+template <class Mem, uint32_t kFeat>
+RT_HD void trav_node_step(const SceneT<Mem, kFeat>& sc, Trav& tr, TravStack& stk) {  // requires trav_in_node(tr)
     const uint32_t n = tr.cur;
     const float4 q0 = sc.node_q(n, 0u), q1 = sc.node_q(n, 1u);
     const float4 q2 = sc.node_q(n, 2u), q3 = sc.node_q(n, 3u);
@@ -498,8 +515,8 @@ RT_HD void trav_node_step(const SceneT<Mem, kLean>& sc, Trav& tr, TravStack& stk
     }
 }
 
-template <class Mem, bool kLean, class Path>
-RT_HD void trav_leaf_test(const SceneT<Mem, kLean>& sc, const Path& path, Trav& tr, uint32_t link) {
+template <class Mem, uint32_t kFeat, class Path>
+RT_HD void trav_leaf_test(const SceneT<Mem, kFeat>& sc, const Path& path, Trav& tr, uint32_t link) {
     const uint32_t first = link & 0x00ffffffu, count = (link >> 24) & 0x7fu;
     for (uint32_t j = first; j < first + count; ++j) {
         const float4 ia = sc.item_a(j), ib = sc.item_b(j);
@@ -511,8 +528,8 @@ RT_HD void trav_leaf_test(const SceneT<Mem, kLean>& sc, const Path& path, Trav& 
         }
     }
 }
-template <class Mem, bool kLean, class Path>
-RT_HD void trav_leaf_step(const SceneT<Mem, kLean>& sc, const Path& path, Trav& tr, const TravStack& stk) {  // requires trav_in_leaf(tr)
+template <class Mem, uint32_t kFeat, class Path>
+RT_HD void trav_leaf_step(const SceneT<Mem, kFeat>& sc, const Path& path, Trav& tr, const TravStack& stk) {  // requires trav_in_leaf(tr)
     trav_leaf_test(sc, path, tr, tr.cur);
     trav_pop(tr, stk);
 }
@@ -547,8 +564,8 @@ RT_HD float rt_max3(float a, float b, float c) { return rt_max(rt_max(a, b), c);
 RT_HD float rt_min3(float a, float b, float c) { return rt_min(rt_min(a, b), c); }
 
 // Call after tr.fo / tr.fd / tr.inv are set (trav_begin, SET_FRAME).
-template <class Mem, bool kLean>
-RT_HD void trav_fast_setup(const SceneT<Mem, kLean>& sc, Trav& tr) {
+template <class Mem, uint32_t kFeat>
+RT_HD void trav_fast_setup(const SceneT<Mem, kFeat>& sc, Trav& tr) {
     const float lo = 7.8886090522101181e-31f, hi = 1.2676506002282294e+30f;  // 2^-100, 2^100
     const float ax = fabsf(tr.inv.x), ay = fabsf(tr.inv.y), az = fabsf(tr.inv.z);
     const float om = rt_max3(fabsf(tr.fo.x), fabsf(tr.fo.y), fabsf(tr.fo.z));
@@ -575,8 +592,8 @@ RT_HD V3 trav_exact_inv(const Trav& tr) {
     return tr.inv;
 }
 
-template <class Mem, bool kLean>
-RT_HD void trav_node_step_fast(const SceneT<Mem, kLean>& sc, Trav& tr, TravStack& stk) {  // requires trav_in_node(tr)
+template <class Mem, uint32_t kFeat>
+RT_HD void trav_node_step_fast(const SceneT<Mem, kFeat>& sc, Trav& tr, TravStack& stk) {  // requires trav_in_node(tr)
     const uint32_t nb = tr.cur * kFastNodeBytes;
     const float4 X = sc.m.ld4(tr.nbx + nb), Y = sc.m.ld4(tr.nby + nb), Z = sc.m.ld4(tr.nbz + nb);  // {near0, far0, near1, far1}
     const float4 L = sc.m.ld4(sc.off_fnodes + 96u + nb);                                            // {link0, link1, m, -}
@@ -604,23 +621,23 @@ RT_HD void trav_node_step_fast(const SceneT<Mem, kLean>& sc, Trav& tr, TravStack
 
 // A leaf of the fast tree: the reference's Aabb::hit (aabb.rs:18-29) on the leaf's own box — the
 // BBOX item kept in front of its primitives — and then the primitives.
-template <class Mem, bool kLean, class Path>
-RT_HD void trav_leaf_visit_fast(const SceneT<Mem, kLean>& sc, const Path& path, Trav& tr, uint32_t link) {
+template <class Mem, uint32_t kFeat, class Path>
+RT_HD void trav_leaf_visit_fast(const SceneT<Mem, kFeat>& sc, const Path& path, Trav& tr, uint32_t link) {
     const uint32_t first = link & 0x00ffffffu;
     const float4 mn = sc.item_a(first - 1u), mx = sc.item_b(first - 1u);
     float start;
     if (slab_test(mn, mx, tr.fo, trav_exact_inv<true>(tr), tr.best_t, start)) trav_leaf_test(sc, path, tr, link);
 }
-template <class Mem, bool kLean, class Path>
-RT_HD void trav_leaf_step_fast(const SceneT<Mem, kLean>& sc, const Path& path, Trav& tr, const TravStack& stk) {  // requires trav_in_leaf(tr)
+template <class Mem, uint32_t kFeat, class Path>
+RT_HD void trav_leaf_step_fast(const SceneT<Mem, kFeat>& sc, const Path& path, Trav& tr, const TravStack& stk) {  // requires trav_in_leaf(tr)
     trav_leaf_visit_fast(sc, path, tr, tr.cur);
     trav_pop(tr, stk);
 }
 
 // Out-of-line copy of prim_hit_t for rare callers (ConstantMedium boundaries).
 struct TimeOnlyView;
-template <class Mem, bool kLean>
-RT_HD_NOINLINE bool prim_hit_outline(const SceneT<Mem, kLean> sc, float4 ia, float4 ib, V3 o, V3 d, float time, uint32_t cur_frame,
+template <class Mem, uint32_t kFeat>
+RT_HD_NOINLINE bool prim_hit_outline(const SceneT<Mem, kFeat> sc, float4 ia, float4 ib, V3 o, V3 d, float time, uint32_t cur_frame,
                                      uint32_t cur_nops, float t_lo, float t_hi, float& t_out);
 
 struct TimeOnlyView {
@@ -628,8 +645,8 @@ struct TimeOnlyView {
     RT_HD float rtime() const { return time; }
 };
 
-template <class Mem, bool kLean>
-RT_HD_NOINLINE bool prim_hit_outline(const SceneT<Mem, kLean> sc, float4 ia, float4 ib, V3 o, V3 d, float time, uint32_t cur_frame,
+template <class Mem, uint32_t kFeat>
+RT_HD_NOINLINE bool prim_hit_outline(const SceneT<Mem, kFeat> sc, float4 ia, float4 ib, V3 o, V3 d, float time, uint32_t cur_frame,
                                      uint32_t cur_nops, float t_lo, float t_hi, float& t_out) {
     return prim_hit_t(sc, ia, ib, o, d, TimeOnlyView{time}, cur_frame, cur_nops, t_lo, t_hi, t_out);
 }
@@ -639,8 +656,8 @@ struct BestHit {
     float t;
     uint32_t item;
 };
-template <class Mem, bool kLean>
-RT_HD_NOINLINE BestHit medium_hit(const SceneT<Mem, kLean> sc, Rng rng, uint32_t bounce, float time, uint32_t i, V3 fo, V3 fd,
+template <class Mem, uint32_t kFeat>
+RT_HD_NOINLINE BestHit medium_hit(const SceneT<Mem, kFeat> sc, Rng rng, uint32_t bounce, float time, uint32_t i, V3 fo, V3 fd,
                                   uint32_t f_id, uint32_t f_nops, float best_t, uint32_t best) {
     const float4 ia = sc.item_a(i);
     const uint32_t mframe = f2u(ia.w) >> 4;
@@ -679,8 +696,8 @@ RT_HD_NOINLINE BestHit medium_hit(const SceneT<Mem, kLean> sc, Rng rng, uint32_t
 // ------------------------------------------------------------------------------------------------
 // Interprets stream items from tr.i until a re-indexed subtree starts (tr.cur = its root) or the
 // stream ends (tr.i = kStreamEnd).
-template <bool kFrames, bool kFast, class Mem, bool kLean, class Path>
-RT_HD void trav_stream(const SceneT<Mem, kLean>& sc, const Path& path, Trav& tr) {
+template <bool kFrames, bool kFast, class Mem, uint32_t kFeat, class Path>
+RT_HD void trav_stream(const SceneT<Mem, kFeat>& sc, const Path& path, Trav& tr) {
     // the last wrapped primitive's frame: the six rects of a rotated prism share one chain
     uint32_t pf_id = tr.f_id;
     V3 po = tr.fo, pd = tr.fd;
@@ -688,7 +705,7 @@ RT_HD void trav_stream(const SceneT<Mem, kLean>& sc, const Path& path, Trav& tr)
     for (;;) {
         const float4 ia = sc.item_a(i);
         const uint32_t kind = f2u(ia.w) & 15u;
-        if (kind == IT_ACCEL) {
+        if ((kFeat & SF_ACCEL) && kind == IT_ACCEL) {
             tr.cur = f2u(ia.x);
             tr.sp = 0;
             i = f2u(ia.w) >> 4;
@@ -696,7 +713,7 @@ RT_HD void trav_stream(const SceneT<Mem, kLean>& sc, const Path& path, Trav& tr)
         } else if (kind == IT_SPHERE || kind == IT_RECT) {
             const float4 ib = sc.item_b(i);
             const uint32_t frame = f2u(ia.w) >> 4;
-            if (!kLean && frame != pf_id) {  // (po, pd) = the ray in this primitive's frame; consecutive items mostly share it
+            if ((kFeat & SF_WRAP) && frame != pf_id) {  // (po, pd) = the ray in this primitive's frame; consecutive items mostly share it
                 if (frame == tr.f_id) {
                     po = tr.fo;
                     pd = tr.fd;
@@ -718,12 +735,12 @@ RT_HD void trav_stream(const SceneT<Mem, kLean>& sc, const Path& path, Trav& tr)
             const float4 ib = sc.item_b(i);
             float start;
             i = slab_test(ia, ib, tr.fo, trav_exact_inv<kFast>(tr), tr.best_t, start) ? i + 1u : (f2u(ia.w) >> 4);
-        } else if (!kLean && kind == IT_MEDIUM) {
+        } else if ((kFeat & SF_MEDIUM) && kind == IT_MEDIUM) {
             const BestHit h = medium_hit(sc, path.rng(), path.bounce(), path.rtime(), i, tr.fo, tr.fd, tr.f_id, tr.f_nops, tr.best_t, tr.best);
             tr.best_t = h.t;
             tr.best = h.item;
             i += 2u;
-        } else if (!kLean && kind == IT_SET_FRAME) {
+        } else if (kFrames && kind == IT_SET_FRAME) {
             if (kFrames) {
                 tr.f_id = f2u(ia.w) >> 4;
                 const uint2 fr = sc.frame(tr.f_id);
@@ -750,8 +767,8 @@ RT_HD void trav_stream(const SceneT<Mem, kLean>& sc, const Path& path, Trav& tr)
 // World::hit_top: the steps above run back to back for one ray.  Returns the index of the winning
 // item (kNoHit if none) and its t.
 // ------------------------------------------------------------------------------------------------
-template <bool kFrames, bool kFast, class Mem, bool kLean>
-RT_HD uint32_t hit_top_stream(const SceneT<Mem, kLean>& sc, const PathState& st, float& best_t_out) {
+template <bool kFrames, bool kFast, class Mem, uint32_t kFeat>
+RT_HD uint32_t hit_top_stream(const SceneT<Mem, kFeat>& sc, const PathState& st, float& best_t_out) {
     Trav tr;
     TravStack stk;
     const PathStateView path{&st};
@@ -759,7 +776,7 @@ RT_HD uint32_t hit_top_stream(const SceneT<Mem, kLean>& sc, const PathState& st,
     if (kFast) trav_fast_setup(sc, tr);
     for (;;) {
         trav_stream<kFrames, kFast>(sc, path, tr);
-        while (tr.cur != kLinkNone) {  // "while-while": lanes stay together in the cheap node loop
+        while ((kFeat & SF_ACCEL) && tr.cur != kLinkNone) {  // "while-while": lanes stay together in the cheap node loop
             if (kFast) {
                 while (trav_in_node(tr)) trav_node_step_fast(sc, tr, stk);
                 if (trav_in_leaf(tr)) trav_leaf_step_fast(sc, path, tr, stk);
@@ -778,8 +795,8 @@ RT_HD uint32_t hit_top_stream(const SceneT<Mem, kLean>& sc, const PathState& st,
 // The body of color()'s loop after hit_top (lib.rs:73-98).  Returns true when the path is finished
 // and `result` holds what color() returns; otherwise st carries the scattered ray.
 // ------------------------------------------------------------------------------------------------
-template <class Mem, bool kLean>
-RT_HD bool shade_and_scatter(const SceneT<Mem, kLean>& sc, const KParams& P, PathState& st, uint32_t best, float best_t, V3& result) {
+template <class Mem, uint32_t kFeat>
+RT_HD bool shade_and_scatter(const SceneT<Mem, kFeat>& sc, const KParams& P, PathState& st, uint32_t best, float best_t, V3& result) {
     result = splat(0.f);
     if (best == kNoHit) {  // lib.rs:100, or the book-1 sky (rtiow_b200.h RTIOW_BG_SKY_GRADIENT)
         if (P.bg_kind == 1u) {
@@ -797,20 +814,20 @@ RT_HD bool shade_and_scatter(const SceneT<Mem, kLean>& sc, const KParams& P, Pat
     uint2 fr;
     fr.x = 0u; fr.y = 0u;
     V3 lo = st.ro, ld = st.rd;
-    if (!kLean && frame != 0u) {
+    if ((kFeat & SF_WRAP) && frame != 0u) {
         fr = sc.frame(frame);
         const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * fr.x, fr.y, lo, ld, st.rtime);
         lo = r.o;
         ld = r.d;
     }
     V3 p, n;
-    if (kLean || kind == IT_SPHERE) {
+    if ((kFeat & SF_SPHERE) && (!(kFeat & (SF_RECT | SF_MEDIUM)) || kind == IT_SPHERE)) {
         if (flags & FL_HAS_OFFSET) lo = lo - mk(ib.x, ib.y, ib.z);
         p = lo + best_t * ld;  // ray.point_at_parameter(t)  object.rs:100
         n = p / ia.x;          // object.rs:104
         if (flags & FL_FLIP) n = -n;
         if (flags & FL_HAS_OFFSET) p = p + mk(ib.x, ib.y, ib.z);
-    } else if (kind == IT_RECT) {
+    } else if ((kFeat & SF_RECT) && (!(kFeat & SF_MEDIUM) || kind == IT_RECT)) {
         p = lo + best_t * ld;  // object.rs:209
         const uint32_t axis = (flags >> 2) & 3u;
         n = mk(axis == 0 ? 1.f : 0.f, axis == 1 ? 1.f : 0.f, axis == 2 ? 1.f : 0.f);
@@ -819,7 +836,7 @@ RT_HD bool shade_and_scatter(const SceneT<Mem, kLean>& sc, const KParams& P, Pat
         p = lo + best_t * ld;
         n = mk(1.f, 0.f, 0.f);
     }
-    if (!kLean && fr.y != 0u) {
+    if ((kFeat & SF_WRAP) && fr.y != 0u) {
         const Ray6 r = frame_ops_hit(sc.m, sc.off_ops + 16u * fr.x, fr.y, p, n);
         p = r.o;
         n = r.d;
@@ -830,7 +847,7 @@ RT_HD bool shade_and_scatter(const SceneT<Mem, kLean>& sc, const KParams& P, Pat
     const uint32_t mkind = f2u(m0.x) & 0xffu;
     const V3 rd = st.rd;
     bool done = false;
-    if (!kLean && mkind == MAT_DIFFUSE_LIGHT) {
+    if ((kFeat & SF_LIGHT) && mkind == MAT_DIFFUSE_LIGHT) {
         // accum = accum + strength * (brightness * emission(p)); no scatter -> return accum  (lib.rs:76,88-91)
         result = splat(0.f) + st.strength * (m0.z * material_texture(sc, m0, m1, p));
         return true;
@@ -838,7 +855,7 @@ RT_HD bool shade_and_scatter(const SceneT<Mem, kLean>& sc, const KParams& P, Pat
     // The scatter draws of this bounce: Vec3::in_unit_sphere (vec3.rs:19-26) for Lambertian, Metal and
     // Isotropic — attempt k reads words x, y, z of SCATTER block k — and word x of block 0 for the
     // Dielectric's reflect-or-refract draw.  One loop, so the Philox rounds exist once in the kernel.
-    const bool wants_sphere = mkind != MAT_DIELECTRIC;
+    const bool wants_sphere = !(kFeat & SF_SPECULAR) || mkind != MAT_DIELECTRIC;
     V3 ius = splat(0.f);
     float draw0;
     for (uint32_t k = 0;; ++k) {
@@ -853,13 +870,13 @@ RT_HD bool shade_and_scatter(const SceneT<Mem, kLean>& sc, const KParams& P, Pat
         st.rd = target - p;
         st.ro = p;
         st.strength = st.strength * material_texture(sc, m0, m1, p);
-    } else if (mkind == MAT_METAL) {           // material.rs:66-81
+    } else if ((kFeat & SF_SPECULAR) && mkind == MAT_METAL) {  // material.rs:66-81
         const V3 refl = reflect(into_unit(rd), n);
         st.rd = refl + m0.z * ius;
         st.ro = p;
         if (dot(st.rd, n) > 0.f) st.strength = st.strength * mk(m1.x, m1.y, m1.z);
         else done = true;                      // absorbed: return accum (= 0)
-    } else if (kLean || mkind == MAT_DIELECTRIC) {  // material.rs:82-107
+    } else if ((kFeat & SF_SPECULAR) && (!(kFeat & SF_ISOTROPIC) || mkind == MAT_DIELECTRIC)) {  // material.rs:82-107
         const float ref_idx = m0.z;
         V3 outward_normal;
         float ni_over_nt, cosine;
@@ -881,7 +898,7 @@ RT_HD bool shade_and_scatter(const SceneT<Mem, kLean>& sc, const KParams& P, Pat
         st.rd = direction;
         st.ro = p;
         st.strength = st.strength * splat(1.f);
-    } else {                                   // Isotropic  material.rs:109-116
+    } else if (kFeat & SF_ISOTROPIC) {         // Isotropic  material.rs:109-116
         st.rd = ius;
         st.ro = p;
         st.strength = st.strength * material_texture(sc, m0, m1, p);

@@ -57,7 +57,7 @@ __device__ __forceinline__ void stage_scene_tma(unsigned char* smem_dst, const u
     }
 }
 
-template <bool kSmem, bool kFrames, bool kFast, bool kLean, int kThreads, int kMinBlocks>
+template <bool kSmem, bool kFrames, bool kFast, uint32_t kFeat, int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __grid_constant__ KParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
     } else {
         mem.base = P.blob;
     }
-    const SceneT<Mem, kLean> sc = scene_views<kLean>(mem, P);
+    const SceneT<Mem, kFeat> sc = scene_views<kFeat>(mem, P);
 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;

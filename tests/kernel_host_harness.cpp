@@ -15,7 +15,7 @@
 // accel = 1: the re-indexed (SAH, ordered) traversal with conservative inner box tests that the device
 // uses by default; 2: the same tree with the reference's exact box test at every node; 0: the plain
 // reference-order stream.
-template <bool kLean>
+template <uint32_t kFeat>
 static int harness_render_impl(const rtiow_scene_desc_t* desc, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny,
                                uint32_t ns, uint64_t seed, uint32_t row_begin, uint32_t row_end, float* out_rgb,
                                float* out_samples, int accel, uint32_t* layout_out, uint32_t row_step, uint32_t row_band) {
@@ -44,7 +44,7 @@ static int harness_render_impl(const rtiow_scene_desc_t* desc, const rtiow_camer
     P.bg_kind = desc->background_kind;
     std::memcpy(P.bg0, desc->background_c0, 12);
     std::memcpy(P.bg1, desc->background_c1, 12);
-    const SceneT<MemPtr, kLean> sc = scene_views<kLean>(MemPtr{blob.data()}, P);
+    const SceneT<MemPtr, kFeat> sc = scene_views<kFeat>(MemPtr{blob.data()}, P);
     for (uint32_t pix = 0; pix < P.npix; ++pix) {
         float acc[3] = {0.f, 0.f, 0.f};
         for (uint32_t s = 0; s < ns; ++s) {
@@ -75,16 +75,28 @@ static int harness_render_impl(const rtiow_scene_desc_t* desc, const rtiow_camer
     return 0;
 }
 
-// accel: low byte as above; bit 8 asks for the spheres-only specialisation of the per-path code (ignored, like in
-// the library, when the scene does not qualify).
+// accel: low byte as above; bit 8 asks for a feature-specialised instantiation of the per-path code (spheres-only or
+// rect-list, path_logic.cuh kFeatSpheres / kFeatRects), chosen like the library does; layout_out[4] = which (0 = general).
 extern "C" __attribute__((visibility("default"))) int harness_render(const rtiow_scene_desc_t* desc, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny,
                               uint32_t ns, uint64_t seed, uint32_t row_begin, uint32_t row_end, float* out_rgb,
                               float* out_samples, int accel, uint32_t* layout_out, uint32_t row_step, uint32_t row_band) {
-    const bool lean = (accel & 0x100) != 0 && rtiow::lean_scene(desc);
+    const bool specialise = (accel & 0x100) != 0;
     accel &= 0xff;
-    if (layout_out) layout_out[4] = lean ? 1u : 0u;
-    return lean ? harness_render_impl<true>(desc, cam, nx, ny, ns, seed, row_begin, row_end, out_rgb, out_samples, accel, layout_out, row_step, row_band)
-                : harness_render_impl<false>(desc, cam, nx, ny, ns, seed, row_begin, row_end, out_rgb, out_samples, accel, layout_out, row_step, row_band);
+    uint32_t profile = 0;
+    if (specialise) {
+        bool has_frames = false, uses_perlin = false;
+        std::string msg;
+        if (int rc = rtiow::validate_desc(desc, &has_frames, &uses_perlin, &msg)) return rc;
+        rtiow::BlobLayout lay{};
+        rtiow::build_blob(desc, uses_perlin, &lay, accel == 1 ? rtiow::kBlobFast : (accel == 2 ? rtiow::kBlobExact : rtiow::kBlobReferenceOrder));
+        const uint32_t needs = rtiow::scene_features(desc) | (lay.n_accel ? static_cast<uint32_t>(rtiow::SF_ACCEL) : 0u);
+        if (!has_frames && (needs & ~rtiow::kFeatSpheres) == 0u) profile = 1;
+        else if (!has_frames && (needs & ~rtiow::kFeatRects) == 0u) profile = 2;
+    }
+    if (layout_out) layout_out[4] = profile;
+    if (profile == 1) return harness_render_impl<rtiow::kFeatSpheres>(desc, cam, nx, ny, ns, seed, row_begin, row_end, out_rgb, out_samples, accel, layout_out, row_step, row_band);
+    if (profile == 2) return harness_render_impl<rtiow::kFeatRects>(desc, cam, nx, ny, ns, seed, row_begin, row_end, out_rgb, out_samples, accel, layout_out, row_step, row_band);
+    return harness_render_impl<rtiow::SF_ALL>(desc, cam, nx, ny, ns, seed, row_begin, row_end, out_rgb, out_samples, accel, layout_out, row_step, row_band);
 }
 
 // hit_top for caller-supplied rays: n rays as {ox, oy, oz, dx, dy, dz, time}; out[2*i] = winning item of the
@@ -102,7 +114,7 @@ extern "C" __attribute__((visibility("default"))) int harness_trace_rays(const r
     P.blob = blob.data();
     P.off_nodes = lay.off_nodes; P.off_frames = lay.off_frames; P.off_ops = lay.off_ops; P.off_mats = lay.off_mats; P.off_tex = lay.off_tex;
     P.off_pvecs = lay.off_pvecs; P.off_pperm = lay.off_pperm; P.off_fnodes = lay.off_fnodes;
-    const SceneT<MemPtr, false> sc = scene_views<false>(MemPtr{blob.data()}, P);
+    const SceneT<MemPtr, SF_ALL> sc = scene_views<SF_ALL>(MemPtr{blob.data()}, P);
     const bool fast = accel == 1;
     for (uint32_t i = 0; i < n; ++i) {
         PathState st;

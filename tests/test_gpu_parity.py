@@ -131,24 +131,25 @@ def test_execution_shape_does_not_change_results():
     world.set_traversal(1)                               # the reference's own visiting order instead of the re-indexed tree
     assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, ref)
     assert world.stats()["accel_subtrees"] == 0
-    assert world.stats()["lean_kernel"] == 0             # kitchen_sink needs the general kernel
+    assert world.stats()["kernel_profile"] == 0          # kitchen_sink needs the general kernel
 
 
-def test_spheres_only_kernel_is_a_pure_specialisation():
-    """book-1 qualifies for the lean megakernel; forcing the general one must give the same bits, in every
-    traversal mode and with the scene in shared or global memory."""
-    nx, ny, ns = 120, 80, 12
-    world, cam = R.build_scene("book1", nx, ny, use_bvh=True)
-    ref = R.par_cast(nx, ny, ns, cam, world).rgb
-    assert world.stats()["lean_kernel"] == 1
-    for spec in (False, True):
-        world.set_specialisation(spec)
-        for trav in (0, 2, 1):
-            world.set_traversal(trav)
-            for fg in (False, True):
-                world.set_tuning(force_global=fg)
-                assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, ref), (spec, trav, fg)
-                assert world.stats()["lean_kernel"] == int(spec)
+def test_specialised_kernels_are_pure_specialisations():
+    """book-1 qualifies for the spheres-only megakernel and the Cornell box for the rect-list one; forcing the
+    general kernel must give the same bits, in every traversal mode and with the scene in shared or global memory."""
+    for name, bvh, profile, nx, ny, ns in (("book1", True, 1, 120, 80, 12), ("cornell", False, 2, 64, 64, 12)):
+        world, cam = R.build_scene(name, nx, ny, use_bvh=bvh)
+        ref = R.par_cast(nx, ny, ns, cam, world).rgb
+        assert world.stats()["kernel_profile"] == profile and world.stats()["block"] == 1024
+        for spec in (False, True):
+            world.set_specialisation(spec)
+            for trav in (0, 2, 1):
+                world.set_traversal(trav)
+                for fg in (False, True):
+                    world.set_tuning(force_global=fg)
+                    assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, ref), (name, spec, trav, fg)
+                    assert world.stats()["kernel_profile"] == (profile if spec else 0)
+        world.close()
 
 
 @pytest.mark.parametrize("name,bvh,size", [("book1", True, (240, 160, 12)), ("final", False, (96, 96, 12)),

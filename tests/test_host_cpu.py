@@ -305,19 +305,22 @@ def test_conservative_box_test_error_bound():
     assert worst * 4 <= 16.0        # the kernel's slack per side leaves a factor of 4
 
 
-def test_spheres_only_specialisation_matches_the_general_code(oracle):
-    """The lean instantiation of the per-path code (SceneT<Mem, true>: rects, wrapper chains, media, lights and
-    procedural textures compiled out) is picked for book-1 only and gives the same bits as the general one."""
+def test_feature_specialisations_match_the_general_code(oracle):
+    """The feature-specialised instantiations of the per-path code (SceneT<Mem, kFeat>: everything the scene
+    cannot contain compiled out) are picked for book-1 (spheres) and the Cornell box (rect list) only, and give
+    the same bits as the general code."""
     nx, ny, ns = 48, 32, 6
-    for name, bvh, qualifies in (("book1", True, True), ("book1", False, True), ("kitchen_sink", True, False), ("cornell", False, False)):
+    for name, bvh, profile in (("book1", True, 1), ("book1", False, 1), ("cornell", False, 2), ("cornell_empty", False, 2),
+                               ("bench_cornell", True, 0), ("kitchen_sink", True, 0), ("final", False, 0), ("volume_test", False, 0)):
         world, cam = R.build_scene(name, nx, ny, use_bvh=bvh)
         lay = np.zeros(5, np.uint32)
         general, gs = H.render(world, cam, nx, ny, ns, want_samples=True, accel=1)
-        lean, ls = H.render(world, cam, nx, ny, ns, want_samples=True, accel=1, lean=True, layout=lay)
-        assert bool(lay[4]) == qualifies, name
-        assert np.array_equal(general.view(np.uint32), lean.view(np.uint32)) and np.array_equal(gs.view(np.uint32), ls.view(np.uint32))
-    want, _, _ = oracle.Scene("book1", nx, ny).render(ns, nthreads=os.cpu_count() or 4)
-    world, cam = R.build_scene("book1", nx, ny, use_bvh=True)
-    for accel in (1, 2, 0):
-        got, _ = H.render(world, cam, nx, ny, ns, accel=accel, lean=True)
-        assert n_diff(got, want) == 0, accel
+        special, ss = H.render(world, cam, nx, ny, ns, want_samples=True, accel=1, lean=True, layout=lay)
+        assert int(lay[4]) == profile, (name, int(lay[4]))
+        assert np.array_equal(general.view(np.uint32), special.view(np.uint32)) and np.array_equal(gs.view(np.uint32), ss.view(np.uint32))
+    for name, bvh in (("book1", True), ("cornell", False)):
+        want, _, _ = oracle.Scene(name, nx, ny, top_level_bvh=bvh).render(ns, nthreads=os.cpu_count() or 4)
+        world, cam = R.build_scene(name, nx, ny, use_bvh=bvh)
+        for accel in (1, 2, 0):
+            got, _ = H.render(world, cam, nx, ny, ns, accel=accel, lean=True)
+            assert n_diff(got, want) == 0, (name, accel)
