@@ -244,3 +244,24 @@ def test_philox_core_matches_curand(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "0 mismatching words" in out.stdout
+
+
+def test_different_seeds_agree_statistically(oracle):
+    """SURVEY §8c rung R3 — the only comparison one could ever make against the Rust binary, whose RNG is seeded from
+    the OS (src/lib.rs:367): renders with different seeds are different bit patterns of the same estimator.  Per-pixel
+    differences between an oracle render (seed A) and a GPU render (seed B), scaled by the per-pixel standard error
+    estimated from the GPU's own per-sample radiance, must look like N(0, 1)."""
+    nx, ny, ns = 96, 64, 64
+    world, cam = R.build_scene("book1", nx, ny)
+    smp = api.render_samples(nx, ny, ns, cam, world, seed=777)[..., :3].astype(np.float64)       # [ny, nx, ns, 3]
+    gpu_mean = smp.mean(axis=2)
+    se = smp.std(axis=2, ddof=1) / np.sqrt(ns)
+    want, _, _ = oracle.Scene("book1", nx, ny).render(ns, seed=12345, nthreads=NT)
+    ok = se > 1e-6                                            # pixels with any variance (not pure sky of one colour)
+    z = (want.astype(np.float64) - gpu_mean)[ok] / (np.sqrt(2.0) * se[ok])
+    assert ok.mean() > 0.5
+    # robust quantiles (a pixel whose 64 samples happen to agree has a tiny standard error: the tails are heavy);
+    # N(0, 1) has median |z| = 0.674 and 90th percentile 1.645 — two oracle seeds give 0.68 and 1.71
+    q50, q90 = np.percentile(np.abs(z), [50, 90])
+    assert 0.55 < q50 < 0.8 and 1.4 < q90 < 2.0, (q50, q90)
+    assert abs((want.astype(np.float64) - gpu_mean).mean()) < 3e-3   # frame means agree
