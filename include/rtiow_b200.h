@@ -16,7 +16,9 @@
  * Conventions: plain pointers and sizes only; all input buffers are caller-owned HOST memory and
  * are copied during the call; every function returns 0 on success or an RTIOW_ERR_* code and
  * leaves a message readable with rtiow_b200_last_error() (thread-local).  A scene handle may be
- * used from one host thread at a time.
+ * used from one host thread at a time and has ONE set of device work buffers: renders of the same scene
+ * enqueued on different CUDA streams (the *_device entry points) are ordered one after the other by
+ * the library, they do not overlap; rtiow_b200_scene_destroy waits for the scene's last render.
  */
 #ifndef RTIOW_B200_H
 #define RTIOW_B200_H
@@ -229,14 +231,28 @@ RTIOW_API int rtiow_b200_render_rows_strided_device(rtiow_scene_t* scene, const 
 RTIOW_API int rtiow_b200_render_samples(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny,
                               uint32_t ns, uint64_t seed, uint32_t row_begin, uint32_t row_end, float* out_samples);
 
-/* print_ppm's per-channel sqrt + to_u8 (src/lib.rs:344-361) on the device: n floats -> n bytes. */
+/* print_ppm's per-channel sqrt + to_u8 (src/lib.rs:344-361) on the device: n floats -> n bytes.
+ * `linear` and `out` are HOST memory (a checker for frames that already live on the host). */
 RTIOW_API int rtiow_b200_ppm_quantise(rtiow_scene_t* scene, const float* linear, size_t n, uint8_t* out);
+
+/* The same quantiser on a frame that is already on the device (the output of rtiow_b200_render_rows_device):
+ * `d_linear` (n floats) and `d_out` (n bytes) are DEVICE memory; enqueued on `cuda_stream`, nothing synchronised. */
+RTIOW_API int rtiow_b200_ppm_quantise_device(rtiow_scene_t* scene, const float* d_linear, size_t n, uint8_t* d_out,
+                                             void* cuda_stream);
+
+/* par_cast followed by print_ppm's quantiser, both on the device: `out_rgb8` (HOST) receives ny*nx*3 bytes, row 0 =
+ * top, exactly the numbers print_ppm writes (src/lib.rs:346-360).  The frame crosses PCIe as bytes, a quarter of
+ * the float frame (C5: 46 MB instead of 184 MB), and the host does no per-pixel arithmetic. */
+RTIOW_API int rtiow_b200_render_ppm(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny, uint32_t ns,
+                                    uint64_t seed, uint8_t* out_rgb8);
 
 /* Synchronises the scene's device and reports the last render. */
 RTIOW_API int rtiow_b200_get_stats(rtiow_scene_t* scene, rtiow_stats_t* out);
 
-/* Tuning knobs (0 = default / automatic): threads per CTA (256, 512 or 768), CTAs per SM, staging budget in MiB,
- * force_global != 0 keeps the scene in global memory even if it fits shared memory. */
+/* Tuning knobs (0 = default / automatic; every call sets all four): threads per CTA (256, 512, 768, or 1024 for the
+ * specialised kernels only), CTAs per SM, per-sample staging budget in MiB (automatic: up to 56 GiB and 70 % of the
+ * free device memory, so that the BASELINE configurations are one pass), force_global != 0 keeps the scene in global
+ * memory even if it fits shared memory.  None of them changes a bit of the image. */
 RTIOW_API int rtiow_b200_set_tuning(rtiow_scene_t* scene, uint32_t cta_threads, uint32_t ctas_per_sm, uint32_t staging_mib,
                           int force_global);
 

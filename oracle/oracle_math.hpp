@@ -85,7 +85,7 @@ inline int32_t f32_as_i32(float x) {
 // from a kernel, and CUDA's own versions round differently, so the parity contract fixes ONE
 // algorithm built from IEEE double +,-,*,/ only (bit-reproducible on any conforming target) and
 // rounds once to f32 at the end.  This file and the product's device header each spell it out
-// independently.  Against glibc these agree to <= 1 ulp (checked in tests/test_oracle_math.py).
+// independently.  Against glibc these agree to <= 1 ulp (checked in tests/test_oracle_kat.py).
 // ---------------------------------------------------------------------------------------------
 
 // ln for material/medium code: object.rs:562 `rng().ln()`.

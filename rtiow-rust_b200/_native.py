@@ -67,6 +67,7 @@ class Stats(C.Structure):
 ABI_SYMBOLS = ("rtiow_b200_abi_version", "rtiow_b200_last_error", "rtiow_b200_scene_validate",
                "rtiow_b200_scene_create", "rtiow_b200_scene_destroy", "rtiow_b200_release_cached_memory", "rtiow_b200_render", "rtiow_b200_render_rows",
                "rtiow_b200_render_rows_device", "rtiow_b200_render_rows_strided_device", "rtiow_b200_render_samples", "rtiow_b200_ppm_quantise",
+               "rtiow_b200_ppm_quantise_device", "rtiow_b200_render_ppm",
                "rtiow_b200_get_stats", "rtiow_b200_set_tuning", "rtiow_b200_set_traversal", "rtiow_b200_set_specialisation")
 
 _abi = None
@@ -99,6 +100,8 @@ def abi():
         L.rtiow_b200_render_rows_strided_device.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, u32, u32, u32, u32, vp, vp]
         L.rtiow_b200_render_samples.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, u32, u32, vp]
         L.rtiow_b200_ppm_quantise.argtypes = [vp, vp, C.c_size_t, vp]
+        L.rtiow_b200_ppm_quantise_device.argtypes = [vp, vp, C.c_size_t, vp, vp]
+        L.rtiow_b200_render_ppm.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, vp]
         L.rtiow_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.rtiow_b200_set_tuning.argtypes = [vp, u32, u32, u32, C.c_int]
         L.rtiow_b200_set_traversal.argtypes = [vp, C.c_int]

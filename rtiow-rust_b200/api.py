@@ -20,7 +20,7 @@ import numpy as np
 
 from . import _native as N
 
-__all__ = ["Camera", "World", "Image", "RtiowError", "build_scene", "par_cast", "cast", "print_ppm", "ppm_bytes",
+__all__ = ["Camera", "World", "Image", "RtiowError", "build_scene", "par_cast", "par_cast_ppm", "cast", "print_ppm", "ppm_bytes", "ppm_bytes_device",
            "SCENES", "DEFAULT_SEED"]
 
 DEFAULT_SEED = 0xDEADBEEF  # src/main.rs:333
@@ -211,6 +211,27 @@ def ppm_bytes(image, world=None, device=0):
     rgb = np.ascontiguousarray(image.rgb if isinstance(image, Image) else image, np.float32)
     out = np.empty(rgb.shape, np.uint8)
     _check(N.abi().rtiow_b200_ppm_quantise(world.gpu(device), rgb.ctypes.data, rgb.size, out.ctypes.data))
+    return out
+
+
+def ppm_bytes_device(frame, world, stream=None):
+    """The same quantiser on a float32 CUDA tensor, result a uint8 CUDA tensor of the same shape; enqueued on `stream`
+    (default: current), nothing synchronised — the float frame never crosses PCIe."""
+    import torch
+    assert frame.is_cuda and frame.dtype == torch.float32 and frame.is_contiguous()
+    dev = frame.device.index or 0
+    out = torch.empty(frame.shape, dtype=torch.uint8, device=frame.device)
+    s = stream if stream is not None else torch.cuda.current_stream(dev)
+    _check(N.abi().rtiow_b200_ppm_quantise_device(world.gpu(dev), C.c_void_p(frame.data_ptr()), frame.numel(),
+                                                  C.c_void_p(out.data_ptr()), C.c_void_p(s.cuda_stream)))
+    return out
+
+
+def par_cast_ppm(nx, ny, ns, camera, world, seed=DEFAULT_SEED, device=0):
+    """par_cast + print_ppm's quantiser in one device-side call (rtiow_b200_render_ppm): uint8 [ny, nx, 3], the numbers
+    print_ppm writes (src/lib.rs:346-360); a quarter of the float frame's bytes come back over PCIe."""
+    out = np.empty((ny, nx, 3), np.uint8)
+    _check(N.abi().rtiow_b200_render_ppm(world.gpu(device), C.byref(camera.rec), nx, ny, ns, seed, out.ctypes.data))
     return out
 
 

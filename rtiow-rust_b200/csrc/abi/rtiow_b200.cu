@@ -65,10 +65,33 @@ struct Workspace {
     static constexpr size_t kBounce = 4u << 20;
     void* pinned[2] = {nullptr, nullptr};
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+    // Renders may be enqueued on the caller's streams: `busy` marks the end of the last one, so that whoever
+    // touches the buffers next (a render on another stream, a scene that inherits this workspace from the
+    // cache, destroy) orders itself after it.
+    cudaEvent_t busy = nullptr;
+    cudaStream_t busy_stream = nullptr;
+    bool busy_recorded = false;
+
+    // Orders `s` after the last render that used these buffers (no-op on the stream that ran it).
+    cudaError_t order_after_last_render(cudaStream_t s) {
+        if (!busy_recorded || s == busy_stream) return cudaSuccess;
+        return cudaStreamWaitEvent(s, busy, 0);
+    }
+    cudaError_t mark_render_end(cudaStream_t s) {
+        cudaError_t e = cudaEventRecord(busy, s);
+        if (e == cudaSuccess) { busy_stream = s; busy_recorded = true; }
+        return e;
+    }
+    // Blocks the host until the last render that used these buffers has finished.
+    void wait_idle() {
+        if (busy_recorded) cudaEventSynchronize(busy);
+        if (stream) cudaStreamSynchronize(stream);
+    }
 
     cudaError_t init(int dev) {
         device = dev;
         cudaError_t e;
+        if ((e = cudaEventCreateWithFlags(&busy, cudaEventDisableTiming)) != cudaSuccess) return e;
         if ((e = cudaMalloc(reinterpret_cast<void**>(&d_counter), sizeof(unsigned int))) != cudaSuccess) return e;
         if ((e = cudaMalloc(reinterpret_cast<void**>(&d_segs), sizeof(unsigned long long))) != cudaSuccess) return e;
         if ((e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
@@ -76,7 +99,8 @@ struct Workspace {
     }
     void destroy() {
         cudaSetDevice(device);
-        if (stream) cudaStreamSynchronize(stream);
+        wait_idle();
+        if (busy) cudaEventDestroy(busy);
         staging.release(); accum.release(); out.release(); samples.release();
         for (DevBuf& b : scene_blob) b.release();
         if (d_counter) cudaFree(d_counter);
@@ -142,6 +166,30 @@ cudaError_t device_info(int device, DeviceInfo* out) {
     return cudaSuccess;
 }
 
+// Per-(kernel, device) launch state, set once: the dynamic shared memory limit is raised to the device's opt-in
+// maximum (the attribute is process-wide per function and device: setting it to each scene's own size before
+// every launch would let two host threads rendering different scenes undercut each other), registers are read once.
+struct KernelInfo {
+    const void* fn;
+    int device;
+    int regs;
+};
+std::mutex g_kernel_mutex;
+std::vector<KernelInfo> g_kernel_info;
+
+cudaError_t kernel_info(const void* fn, int device, int max_smem_optin, int* regs) {
+    std::lock_guard<std::mutex> lock(g_kernel_mutex);
+    for (const KernelInfo& k : g_kernel_info)
+        if (k.fn == fn && k.device == device) { *regs = k.regs; return cudaSuccess; }
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin)) != cudaSuccess) return e;
+    cudaFuncAttributes fa{};
+    if ((e = cudaFuncGetAttributes(&fa, fn)) != cudaSuccess) return e;
+    g_kernel_info.push_back(KernelInfo{fn, device, fa.numRegs});
+    *regs = fa.numRegs;
+    return cudaSuccess;
+}
+
 std::mutex g_ws_mutex;
 std::vector<Workspace*> g_ws_cache;
 constexpr size_t kWsCachePerDevice = 2;
@@ -169,7 +217,7 @@ Workspace* ws_acquire(int device, cudaError_t* err) {
 void ws_release(Workspace* w) {
     if (!w) return;
     cudaSetDevice(w->device);
-    cudaStreamSynchronize(w->stream);
+    w->wait_idle();  // also renders enqueued on the caller's streams (rtiow_b200_render_rows_device)
     {
         std::lock_guard<std::mutex> lock(g_ws_mutex);
         size_t same = 0;
@@ -237,12 +285,15 @@ struct rtiow_scene {
     uint32_t events_used = 0;
 
     // tuning
-    uint32_t cta_threads = 0, ctas_per_sm = 0, staging_mib = 2048, sample_chunk = 0;
+    uint32_t cta_threads = 0, ctas_per_sm = 0, staging_mib = 0, sample_chunk = 0;
     bool force_global = false;
     uint32_t features = 0;         // scene_blob.hpp scene_features()
     bool specialise = true;        // use a kernel compiled for a subset of features when the scene allows (same image)
     uint32_t refill_lanes = 0;     // 0 = automatic
     bool costly_segments = false;  // the scene has wrapper frames on subtrees or constant media
+    bool bottom_first = true;      // unit order (RTIOW_B200_UNIT_ORDER=0: top rows first)
+    int phase_sync = -1;           // -1 = automatic (RTIOW_B200_PHASE_SYNC, read once at scene_create)
+    uint32_t phase_group_env = 0;  // RTIOW_B200_PHASE_GROUP, 0 = automatic
 
     // last render
     rtiow_stats_t stats{};
@@ -305,10 +356,21 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     const uint32_t n_rows = n_full * band + std::min(rest, band);
     const uint64_t npix64 = static_cast<uint64_t>(n_rows) * nx;
     const uint32_t npix = static_cast<uint32_t>(npix64);
-    const uint64_t budget = static_cast<uint64_t>(s->staging_mib) << 20;
-    uint32_t s_pass = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(ns, budget / (npix64 * 16))));
-    const uint32_t n_pass = (ns + s_pass - 1) / s_pass;
     Workspace& W = *s->ws;
+    CK(W.order_after_last_render(stream));
+    // Per-sample staging budget.  Automatic: up to 56 GiB, at most 70 % of what is free — a B200 has 180 GB and a
+    // pass boundary costs a kernel tail, so C3 (10 GB), C4 (51 GB) and one rank's share of C5 (15 GB) are single passes.
+    uint64_t budget = static_cast<uint64_t>(s->staging_mib) << 20;
+    if (s->staging_mib == 0) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        budget = std::min<uint64_t>(56ull << 30, (static_cast<uint64_t>(free_b) + W.staging.cap) / 10 * 7);
+        budget = std::max<uint64_t>(budget, 64ull << 20);
+    }
+    // passes of equal size (the last one is not a sliver)
+    const uint32_t s_max = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(ns, budget / (npix64 * 16))));
+    const uint32_t n_pass = (ns + s_max - 1) / s_max;
+    const uint32_t s_pass = (ns + n_pass - 1) / n_pass;
     CK(W.staging.reserve(npix64 * s_pass * 16));
     CK(W.accum.reserve(npix64 * 16));
 
@@ -338,7 +400,8 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
                                    : rtiow::pick_plain_global(s->has_frames, fast, profile, threads);
     if (!var.fn) return set_err(RTIOW_ERR_INVALID_ARG, "no kernel instantiation for this cta_threads");
     const size_t dyn_smem = smem ? B.bytes : 0;
-    CK(cudaFuncSetAttribute(var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_smem)));
+    int num_regs = 0;
+    CK(kernel_info(reinterpret_cast<const void*>(var.fn), s->device, s->max_smem_optin, &num_regs));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var.fn, var.threads, dyn_smem));
     if (occ < 1) return set_err(RTIOW_ERR_CUDA, "render kernel does not fit on an SM");
@@ -350,8 +413,6 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     // no more CTAs than there is work for: a warp takes at least one unit (one sample of one tile)
     const uint64_t min_units = static_cast<uint64_t>(n_groups) * std::min(s_pass, ns);
     grid = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(grid, (min_units + warps_per_cta - 1) / warps_per_cta)));
-    cudaFuncAttributes fa{};
-    CK(cudaFuncGetAttributes(&fa, var.fn));
 
     KParams P{};
     P.blob = B.d;
@@ -372,12 +433,11 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     // a 32 KB L1.5 I-cache.  Two CTA barriers per round (before hit_top, before shading) keep the 24 warps in the
     // same phase, i.e. the same few KB of code: final scene +16 %; book-1 and Cornell, whose hot set fits, lose 8-30 %.
     // Named barriers over half the CTA (12 warps) wait a little less than __syncthreads and keep the locality.
-    P.phase_sync = std::getenv("RTIOW_B200_PHASE_SYNC") ? static_cast<uint32_t>(std::atoi(std::getenv("RTIOW_B200_PHASE_SYNC")))
-                                                         : (s->costly_segments ? 2u : 0u);
+    P.phase_sync = s->phase_sync >= 0 ? static_cast<uint32_t>(s->phase_sync) : (s->costly_segments ? 2u : 0u);
     P.phase_group = static_cast<uint32_t>(var.threads) / 32u;
     if (P.phase_sync != 0u && P.phase_group % 2u == 0u) P.phase_group /= 2u;  // two barrier groups per CTA: measured best
-    if (const char* env = std::getenv("RTIOW_B200_PHASE_GROUP")) {
-        const uint32_t g = static_cast<uint32_t>(std::max(1, std::atoi(env)));
+    if (s->phase_group_env) {
+        const uint32_t g = s->phase_group_env;
         if (P.phase_group % g == 0 && P.phase_group / g <= 15) P.phase_group = g;
     }
     // Idle lanes get new pixel-samples once `refill_thr` lanes of the warp wait: generating camera rays costs the
@@ -386,6 +446,7 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     // Measured (profiles/r01/sweep_v9_refill_threshold.log): book-1 best at 12, Cornell at 4, final at 1.
     P.refill_thr = s->refill_lanes ? s->refill_lanes : (s->costly_segments ? 1u : (s->bg_kind == RTIOW_BG_SKY_GRADIENT ? 12u : 4u));
 
+    P.bottom_first = s->bottom_first ? 1u : 0u;
     // Work unit = s_chunk samples of one tile.  The kernel ends when the last warp finishes its last unit, so
     // a unit must be a small fraction of a warp's share: the largest chunk of 8, 4, 2, 1 that still leaves
     // every resident warp ~48 units (one GPU at C2: 8; an eighth of the frame on each of 8 GPUs: 1).
@@ -432,6 +493,7 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
         }
         CK(cudaEventRecord(W.events[s->events_used++], stream));
     }
+    CK(W.mark_render_end(stream));
     s->stats = rtiow_stats_t{};
     s->stats.samples = npix64 * ns;
     s->stats.kernel_launches = launches;
@@ -443,7 +505,7 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     s->stats.grid = grid;
     s->stats.block = static_cast<uint32_t>(var.threads);
     s->stats.dyn_smem_bytes = static_cast<uint32_t>(dyn_smem);
-    s->stats.regs_per_thread = static_cast<uint32_t>(fa.numRegs);
+    s->stats.regs_per_thread = static_cast<uint32_t>(num_regs);
     s->stats.kernel_profile = profile;
     s->stats.traversal = static_cast<uint32_t>(mode == rtiow::kBlobFast ? RTIOW_TRAVERSAL_REINDEXED
                                                : (mode == rtiow::kBlobExact ? RTIOW_TRAVERSAL_REINDEXED_EXACT : RTIOW_TRAVERSAL_REFERENCE_ORDER));
@@ -515,6 +577,9 @@ int rtiow_b200_scene_create(const rtiow_scene_desc_t* d, int device, rtiow_scene
     if (const char* env = std::getenv("RTIOW_B200_TRAVERSAL")) s->traversal = std::min(2, std::max(0, std::atoi(env)));
     if (const char* env = std::getenv("RTIOW_B200_SPECIALISE")) s->specialise = std::atoi(env) != 0;
     if (const char* env = std::getenv("RTIOW_B200_REFILL_LANES")) s->refill_lanes = static_cast<uint32_t>(std::min(32, std::max(0, std::atoi(env))));
+    if (const char* env = std::getenv("RTIOW_B200_UNIT_ORDER")) s->bottom_first = std::atoi(env) != 0;
+    if (const char* env = std::getenv("RTIOW_B200_PHASE_SYNC")) s->phase_sync = std::max(0, std::atoi(env));
+    if (const char* env = std::getenv("RTIOW_B200_PHASE_GROUP")) s->phase_group_env = static_cast<uint32_t>(std::max(1, std::atoi(env)));
     if (const char* env = std::getenv("RTIOW_B200_SAMPLE_CHUNK")) s->sample_chunk = static_cast<uint32_t>(std::max(0, std::atoi(env)));
     {   // build + upload the blob of the selected traversal now, so that render calls only launch
         const rtiow::BlobMode mode = s->traversal == RTIOW_TRAVERSAL_REFERENCE_ORDER ? rtiow::kBlobReferenceOrder
@@ -555,7 +620,7 @@ int rtiow_b200_set_tuning(rtiow_scene_t* s, uint32_t cta_threads, uint32_t ctas_
     }
     s->cta_threads = cta_threads;
     s->ctas_per_sm = ctas_per_sm;
-    if (staging_mib) s->staging_mib = staging_mib;
+    s->staging_mib = staging_mib;
     s->force_global = force_global != 0;
     return RTIOW_OK;
 }
@@ -627,6 +692,32 @@ int rtiow_b200_ppm_quantise(rtiow_scene_t* s, const float* linear, size_t n, uin
         static_cast<const float*>(W.out.p), static_cast<unsigned char*>(W.samples.p), n);
     CK(cudaGetLastError());
     CK(W.copy_to_host(out, W.samples.p, n));
+    return RTIOW_OK;
+}
+
+int rtiow_b200_ppm_quantise_device(rtiow_scene_t* s, const float* d_linear, size_t n, uint8_t* d_out, void* cuda_stream) {
+    if (!s || !d_linear || !d_out || n == 0) return set_err(RTIOW_ERR_INVALID_ARG, "null argument");
+    CK(cudaSetDevice(s->device));
+    rtiow::ppm_quantise_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        d_linear, d_out, n);
+    CK(cudaGetLastError());
+    return RTIOW_OK;
+}
+
+int rtiow_b200_render_ppm(rtiow_scene_t* s, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny, uint32_t ns, uint64_t seed,
+                          uint8_t* out_rgb8) {
+    if (int rc = check_render_args(s, cam, nx, ny, ns, 0, ny, out_rgb8)) return rc;
+    CK(cudaSetDevice(s->device));
+    const size_t n = static_cast<size_t>(ny) * nx * 3;
+    Workspace& W = *s->ws;
+    CK(W.out.reserve(n * sizeof(float)));
+    CK(W.samples.reserve(n));
+    if (int rc = enqueue_render(s, cam, nx, ny, ns, seed, 0, ny, static_cast<float*>(W.out.p), nullptr, W.stream)) return rc;
+    rtiow::ppm_quantise_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, W.stream>>>(
+        static_cast<const float*>(W.out.p), static_cast<unsigned char*>(W.samples.p), n);
+    CK(cudaGetLastError());
+    CK(W.mark_render_end(W.stream));
+    CK(W.copy_to_host(out_rgb8, W.samples.p, n));  // a quarter of the float frame's bytes over PCIe
     return RTIOW_OK;
 }
 

@@ -47,6 +47,7 @@ struct KParams {
     uint32_t refill_thr;        // idle lanes are handed new pixel-samples once this many of a warp wait (>= 1)
     uint32_t phase_sync;        // barriers per round: 1 = before hit_top, 2 = also before shading (code-fetch locality)
     uint32_t phase_group;       // warps per barrier group (divides the CTA's warp count)
+    uint32_t bottom_first;      // work units are handed out from the last tile to the first
     float4* staging;            // [s_count][npix] {r, g, b, segments}
     unsigned int* work_counter;
 };

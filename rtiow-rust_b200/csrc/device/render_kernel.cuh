@@ -120,7 +120,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
                 if (lane == 0) u = atomicAdd(P.work_counter, 1u);
                 u = __shfl_sync(0xffffffffu, u, 0);
                 if (u >= P.n_units) { exhausted = true; break; }
-                // unit u = samples [c * s_chunk, ...) of tile g; small units keep the tail short
+                // unit u = samples [c * s_chunk, ...) of tile g; small units keep the tail short.  Tiles are handed out
+                // from the BOTTOM of the row block: the kernel ends when the last warp finishes its last unit, and in the
+                // reference's scenes the cheap pixels (sky, one segment) are at the top — they make the better tail.
+                if (P.bottom_first != 0u) u = P.n_units - 1u - u;
                 const uint32_t g = u / P.n_chunks, c = u - g * P.n_chunks;
                 const uint32_t ty = g / P.tiles_x;
                 pool_x0 = (g - ty * P.tiles_x) * kTileW;

@@ -88,10 +88,12 @@ class ShardBuffers:
     """Device buffers of one rank, allocated once: `mine` (this rank's packed rows, padded to max_rows),
     `parts` (everybody's), `frame` (the assembled image)."""
 
-    def __init__(self, nx, ny, shard, device):
+    def __init__(self, nx, ny, shard, device, world=None):
         import torch
         self.shard = shard
         self.frame = torch.empty((ny, nx, 3), dtype=torch.float32, device=device)
+        self.exchange = "none (one rank)" if shard.world_size == 1 else "one NCCL all_gather_into_tensor of the packed rows" + (
+            " + one strided de-interleave copy" if (shard.interleaved or not shard.uniform) else ", in place")
         if shard.world_size == 1:
             self.mine = self.frame
             self.parts = None
@@ -101,6 +103,10 @@ class ShardBuffers:
         else:
             self.parts = None
             self.mine = self.frame[shard.begin:shard.end]
+
+
+    def close(self):
+        self.frame = self.mine = self.parts = None
 
 
 def render_sharded_device(nx, ny, ns, camera, world, bufs, seed=api.DEFAULT_SEED):

@@ -1,11 +1,12 @@
 #!/usr/bin/env python
 """Summarise one `ncu --set full` capture of the render megakernel for profiles/.
 
-  python scripts/ncu_summary.py gpurun_out/prof_render.ncu-rep profiles/r01/v5 [librtiow_b200.so kernel-substring]
+  NCU_WORKLOAD=C2 NCU_SAMPLES=48000000 python scripts/ncu_summary.py gpurun_out/prof_render.ncu-rep profiles/r02/v13 [librtiow_b200.so kernel-substring]
 
 Writes <prefix>_render_kernel_ncu_full.json (selected raw metrics), <prefix>_by_line.txt (executed
 warp instructions / stall samples per source function and line, when the .so is given) and
-refreshes profiles/ncu_summary.json (DRAM bytes per launch, read by bench.py's roofline.traffic).
+refreshes the NCU_WORKLOAD entry of profiles/ncu_summary.json (per-sample DRAM bytes and warp instructions, issue-slot
+utilisation, lanes per instruction: read by bench.py's `roofline`; NCU_SAMPLES = pixel-samples of the captured launch).
 """
 import csv
 import io
@@ -44,10 +45,21 @@ def to_bytes(m):
 
 
 dram = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
-# profiles/ncu_summary.json feeds bench.py's roofline.traffic: only a capture of the headline workload (C2) may refresh it
-with open(os.path.join(ROOT, "profiles", "ncu_summary.json") if not os.environ.get("NCU_SUMMARY_KEEP") else os.devnull, "w") as f:
-    json.dump({"render_kernel_dram_bytes_per_launch": dram, "source": os.path.relpath(prefix + "_render_kernel_ncu_full.json", ROOT),
-               "kernel_ms_under_ncu": float(out["gpu__time_duration.sum"]["value"])}, f, indent=1)
+# profiles/ncu_summary.json feeds bench.py's `roofline`: one entry per BASELINE workload, refreshed by a capture of that workload
+wl, n_samples = os.environ.get("NCU_WORKLOAD"), float(os.environ.get("NCU_SAMPLES", "0"))
+if wl and n_samples > 0:
+    path = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    table = json.load(open(path)) if os.path.exists(path) else {}
+    fnum = lambda m: float(out[m]["value"].replace(",", ""))  # noqa: E731
+    table[wl] = {"kernel": out["Kernel Name"]["value"], "samples_in_capture": n_samples,
+                 "dram_bytes_per_sample": dram / n_samples,
+                 "warp_inst_per_sample": fnum("smsp__inst_executed.sum") / n_samples,
+                 "issue_slot_frac": fnum("smsp__issue_active.avg.pct_of_peak_sustained_active") / 100.0,
+                 "lanes_per_inst": fnum("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                 "kernel_ms_under_ncu": fnum("gpu__time_duration.sum"),
+                 "source": os.path.relpath(prefix + "_render_kernel_ncu_full.json", ROOT)}
+    with open(path, "w") as f:
+        json.dump(table, f, indent=1)
 if len(sys.argv) > 4:
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     tmp = prefix + "_source.tmp.csv"

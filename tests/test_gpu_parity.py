@@ -230,6 +230,83 @@ def test_c2_full_size_properties(oracle):
     assert 2.0 < st["segments"] / st["samples"] < 3.2
 
 
+@pytest.mark.parametrize("name,ns,bands", [("cornell", 60, (0, 262, 530, 796)), ("final", 36, (0, 300, 520, 796))])
+def test_c3_c4_full_frame_multi_pass_bands_bit_exact(oracle, name, ns, bands):
+    """BASELINE.json configs[2] and [3] at their full 800x800 frame, in several staging passes (the code path the
+    1000 / 5000 spp renders take when the per-sample staging does not fit): scanline bands float-for-float against the
+    oracle, and the pass split must not move a bit."""
+    nx = ny = 800
+    world, cam = R.build_scene(name, nx, ny, use_bvh=False)          # USE_BVH = false, src/main.rs:321
+    world.set_tuning(staging_mib=160)                                 # 800*800*16 B = 9.8 MiB per sample -> 16 samples per pass
+    multi = R.par_cast(nx, ny, ns, cam, world).rgb
+    st = world.stats()
+    assert st["passes"] >= 3 and st["samples"] == nx * ny * ns
+    sc = oracle.Scene(name, nx, ny, top_level_bvh=False)
+    for r0 in bands:
+        want, _, _ = sc.render(ns, rows=(r0, r0 + 4), nthreads=NT)
+        assert n_diff(multi[r0:r0 + 4], want) == 0, (name, r0)
+    world.set_tuning()                                                # automatic budget: one pass
+    single = R.par_cast(nx, ny, ns, cam, world).rgb
+    assert world.stats()["passes"] == 1 and bits_equal(single, multi)
+    assert np.isfinite(multi).all() and multi.min() >= 0.0
+
+
+def test_c5_frame_shape_bands_bit_exact(oracle):
+    """BASELINE.json configs[4]'s 4800x3200 frame (reduced spp), rendered as the 8 interleaved band shards the
+    8-GPU run uses and assembled: bands against the oracle, and the assembled frame against the one-launch frame."""
+    from rtiow_rust_b200 import dist as rdist
+    import torch
+    nx, ny, ns, G = 4800, 3200, 3, 8
+    world, cam = R.build_scene("book1", nx, ny)
+    full = R.par_cast(nx, ny, ns, cam, world).rgb
+    sc = oracle.Scene("book1", nx, ny)
+    for r0 in (0, 1597, 2600, 3196):
+        want, _, _ = sc.render(ns, rows=(r0, r0 + 4), nthreads=NT)
+        assert n_diff(full[r0:r0 + 4], want) == 0, r0
+    shards = [rdist.RowShard(ny, r, G) for r in range(G)]
+    parts = torch.zeros((G, shards[0].max_rows, nx, 3), dtype=torch.float32, device="cuda:0")
+    for r, sh in enumerate(shards):
+        api.render_rows_device(nx, ny, ns, cam, world, parts[r], (sh.begin, sh.end), row_step=sh.step, row_band=sh.band)
+    torch.cuda.synchronize()
+    assert bits_equal(rdist.assemble(parts, shards[0], xp=None).cpu().numpy(), full)
+
+
+@pytest.mark.parametrize("G", [2, 3, 4, 8])
+def test_band_shards_of_every_world_size_assemble_to_the_same_bits(G):
+    """The multi-GPU partition (dist.RowShard + assemble), every rank rendered on this one GPU: identical to G = 1."""
+    from rtiow_rust_b200 import dist as rdist
+    import torch
+    nx, ny, ns = 300, 203, 6                      # ny not a multiple of the band height or of G
+    world, cam = R.build_scene("final", nx, ny, use_bvh=False)
+    full = R.par_cast(nx, ny, ns, cam, world).rgb
+    for interleaved in (True, False):
+        shards = [rdist.RowShard(ny, r, G, interleaved=interleaved) for r in range(G)]
+        parts = torch.zeros((G, shards[0].max_rows, nx, 3), dtype=torch.float32, device="cuda:0")
+        for r, sh in enumerate(shards):
+            if sh.n_rows:
+                api.render_rows_device(nx, ny, ns, cam, world, parts[r], (sh.begin, sh.end), row_step=sh.step, row_band=sh.band)
+        torch.cuda.synchronize()
+        assert bits_equal(rdist.assemble(parts, shards[0], xp=None).cpu().numpy(), full), (G, interleaved)
+
+
+def test_print_ppm_bytes_on_device(oracle):
+    """print_ppm's sqrt + to_u8 (src/lib.rs:344-361) without the float frame leaving the device: render_ppm and the
+    device-resident quantiser give exactly the bytes the Rust binary would print for the oracle's frame."""
+    import torch
+    nx, ny, ns = 200, 120, 10
+    world, cam = R.build_scene("book1", nx, ny)
+    want = oracle.ppm_quantise(oracle.Scene("book1", nx, ny).render(ns, nthreads=NT)[0])
+    got = api.par_cast_ppm(nx, ny, ns, cam, world)
+    assert got.dtype == np.uint8 and np.array_equal(got.astype(np.int32), want)
+    frame = torch.empty((ny, nx, 3), dtype=torch.float32, device="cuda:0")
+    api.render_rows_device(nx, ny, ns, cam, world, frame, (0, ny))
+    q = api.ppm_bytes_device(frame, world)
+    torch.cuda.synchronize()
+    assert np.array_equal(q.cpu().numpy().astype(np.int32), want)
+    edge = torch.tensor([0.0, 1.0, 4.0, -1.0, float("nan"), float("inf"), 0.25, 1e-30], device="cuda:0")
+    assert api.ppm_bytes_device(edge, world).cpu().tolist() == [0, 255, 255, 0, 0, 255, 127, 0]
+
+
 def test_philox_core_matches_curand(tmp_path):
     """The RNG core of the render path (rt_math.cuh philox4x32_10) against NVIDIA's independent implementation
     (curand_Philox4x32_10) on 4 M (counter, key) pairs: pins the generator to something that is not ours."""
