@@ -182,9 +182,11 @@ cudaError_t kernel_info(const void* fn, int device, int max_smem_optin, int* reg
     for (const KernelInfo& k : g_kernel_info)
         if (k.fn == fn && k.device == device) { *regs = k.regs; return cudaSuccess; }
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin)) != cudaSuccess) return e;
     cudaFuncAttributes fa{};
     if ((e = cudaFuncGetAttributes(&fa, fn)) != cudaSuccess) return e;
+    // static + dynamic shared memory share the opt-in limit
+    const int dyn_max = max_smem_optin - static_cast<int>(fa.sharedSizeBytes);
+    if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max)) != cudaSuccess) return e;
     g_kernel_info.push_back(KernelInfo{fn, device, fa.numRegs});
     *regs = fa.numRegs;
     return cudaSuccess;

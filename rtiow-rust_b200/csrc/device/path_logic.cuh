@@ -22,7 +22,9 @@ constexpr float kF32Min = -3.402823466e+38f;  // std::f32::MIN
 constexpr uint32_t kNoHit = 0xffffffffu;
 
 // item kinds / flags mirror include/rtiow_b200.h
-enum : uint32_t { IT_END = 0, IT_BBOX = 1, IT_SPHERE = 2, IT_RECT = 3, IT_MEDIUM = 4, IT_SET_FRAME = 5, IT_ACCEL = 6 };
+enum : uint32_t { IT_END = 0, IT_BBOX = 1, IT_SPHERE = 2, IT_RECT = 3, IT_MEDIUM = 4, IT_SET_FRAME = 5, IT_PRISM = 6, IT_ACCEL = 7 };
+// The winning item of a hit_top call is `item | face << 28` (face = which of a prism's six rects won, else 0).
+constexpr uint32_t kItemMask = 0x0fffffffu;
 constexpr uint32_t kLinkLeafBit = 0x80000000u, kLinkNone = 0x7fffffffu;  // accel_build.hpp
 constexpr int kStackDepth = 32;
 enum : uint32_t { FL_HAS_OFFSET = 1u, FL_FLIP = 2u };
@@ -263,12 +265,29 @@ RT_HD bool rect_hit_t(V3 o, V3 d, uint32_t axis, float4 ia, float4 ib, float t_l
     return rect_hit_axis(o.z, d.z, o.x, d.x, o.y, d.y, ia, ib, t_lo, t_hi, t_out);
 }
 
+// rect_prism (object.rs:420-473) as ONE record {p0, p1}: the six Rect::hit calls of its And tree (object.rs:396-410),
+// in the tree's visiting order — z = p1.z, y = p1.y, x = p1.x, then the FlipNormals faces z = p0.z, y = p0.y,
+// x = p0.x — each with the arithmetic of rect_hit_axis and the range's end shrunk to the last accepted hit
+// (`hit1.or(hit0)`: the last accepted face wins).  `face` = its position in that order.
+RT_HD bool prism_hit_t(V3 o, V3 d, float4 ia, float4 ib, float t_lo, float t_hi, float& t_out, uint32_t& face) {
+    bool hit = false;
+    float t;
+    if (rect_hit_axis(o.z, d.z, o.x, d.x, o.y, d.y, make_float4(ib.z, ia.x, ib.x, 0.f), make_float4(ia.y, ib.y, 0.f, 0.f), t_lo, t_hi, t)) { t_hi = t; face = 0u; hit = true; }
+    if (rect_hit_axis(o.y, d.y, o.x, d.x, o.z, d.z, make_float4(ib.y, ia.x, ib.x, 0.f), make_float4(ia.z, ib.z, 0.f, 0.f), t_lo, t_hi, t)) { t_hi = t; face = 1u; hit = true; }
+    if (rect_hit_axis(o.x, d.x, o.y, d.y, o.z, d.z, make_float4(ib.x, ia.y, ib.y, 0.f), make_float4(ia.z, ib.z, 0.f, 0.f), t_lo, t_hi, t)) { t_hi = t; face = 2u; hit = true; }
+    if (rect_hit_axis(o.z, d.z, o.x, d.x, o.y, d.y, make_float4(ia.z, ia.x, ib.x, 0.f), make_float4(ia.y, ib.y, 0.f, 0.f), t_lo, t_hi, t)) { t_hi = t; face = 3u; hit = true; }
+    if (rect_hit_axis(o.y, d.y, o.x, d.x, o.z, d.z, make_float4(ia.y, ia.x, ib.x, 0.f), make_float4(ia.z, ib.z, 0.f, 0.f), t_lo, t_hi, t)) { t_hi = t; face = 4u; hit = true; }
+    if (rect_hit_axis(o.x, d.x, o.y, d.y, o.z, d.z, make_float4(ia.x, ia.y, ib.y, 0.f), make_float4(ia.z, ib.z, 0.f, 0.f), t_lo, t_hi, t)) { t_hi = t; face = 5u; hit = true; }
+    t_out = t_hi;
+    return hit;
+}
+
 // Any primitive item against a ray (o, d) that is already in frame `cur_frame` (whose chain has
 // `cur_nops` ops, a prefix of the item's own chain): the item's remaining wrappers are applied
 // first, exactly like the nested Object::hit calls.
 template <class Mem, uint32_t kFeat, class Path>
 RT_HD bool prim_hit_t(const SceneT<Mem, kFeat>& sc, float4 ia, float4 ib, V3 o, V3 d, const Path& path, uint32_t cur_frame,
-                      uint32_t cur_nops, float t_lo, float t_hi, float& t_out) {
+                      uint32_t cur_nops, float t_lo, float t_hi, float& t_out, uint32_t& face) {
     const uint32_t kind = f2u(ia.w) & 15u;
     const uint32_t frame = f2u(ia.w) >> 4;
     const uint32_t flags = f2u(ib.w) >> 24;
@@ -284,7 +303,10 @@ RT_HD bool prim_hit_t(const SceneT<Mem, kFeat>& sc, float4 ia, float4 ib, V3 o, 
         if (flags & FL_HAS_OFFSET) o = o - mk(ib.x, ib.y, ib.z);
         return sphere_hit_t(o, d, ia.x, t_lo, t_hi, t_out);
     }
-    if (kFeat & SF_RECT) return rect_hit_t(o, d, (flags >> 2) & 3u, ia, ib, t_lo, t_hi, t_out);
+    if (kFeat & SF_RECT) {
+        if (kind == IT_PRISM) return prism_hit_t(o, d, ia, ib, t_lo, t_hi, t_out, face);
+        return rect_hit_t(o, d, (flags >> 2) & 3u, ia, ib, t_lo, t_hi, t_out);
+    }
     return false;
 }
 
@@ -521,11 +543,12 @@ RT_HD void trav_leaf_test(const SceneT<Mem, kFeat>& sc, const Path& path, Trav& 
     const uint32_t first = link & 0x00ffffffu, count = (link >> 24) & 0x7fu;
     for (uint32_t j = first; j < first + count; ++j) {
         const float4 ia = sc.item_a(j), ib = sc.item_b(j);
-        const float t_hi = (tr.best != kNoHit && j < tr.best) ? next_up_pos(tr.best_t) : tr.best_t;
+        const float t_hi = (tr.best != kNoHit && j < (tr.best & kItemMask)) ? next_up_pos(tr.best_t) : tr.best_t;
         float t;
-        if (prim_hit_t(sc, ia, ib, tr.fo, tr.fd, path, tr.f_id, tr.f_nops, kNear, t_hi, t)) {
+        uint32_t face = 0u;
+        if (prim_hit_t(sc, ia, ib, tr.fo, tr.fd, path, tr.f_id, tr.f_nops, kNear, t_hi, t, face)) {
             tr.best_t = t;
-            tr.best = j;
+            tr.best = j | (face << 28);
         }
     }
 }
@@ -649,7 +672,8 @@ struct TimeOnlyView {
 template <class Mem, uint32_t kFeat>
 RT_HD_NOINLINE bool prim_hit_outline(const SceneT<Mem, kFeat> sc, float4 ia, float4 ib, V3 o, V3 d, float time, uint32_t cur_frame,
                                      uint32_t cur_nops, float t_lo, float t_hi, float& t_out) {
-    return prim_hit_t(sc, ia, ib, o, d, TimeOnlyView{time}, cur_frame, cur_nops, t_lo, t_hi, t_out);
+    uint32_t face = 0u;
+    return prim_hit_t(sc, ia, ib, o, d, TimeOnlyView{time}, cur_frame, cur_nops, t_lo, t_hi, t_out, face);
 }
 
 // ConstantMedium::hit (object.rs:543-575); item i is the medium, item i+1 its boundary primitive.
@@ -711,7 +735,7 @@ RT_HD void trav_stream(const SceneT<Mem, kFeat>& sc, const Path& path, Trav& tr)
             tr.sp = 0;
             i = f2u(ia.w) >> 4;
             break;
-        } else if (kind == IT_SPHERE || kind == IT_RECT) {
+        } else if (kind == IT_SPHERE || kind == IT_RECT || ((kFeat & SF_RECT) && kind == IT_PRISM)) {
             const float4 ib = sc.item_b(i);
             const uint32_t frame = f2u(ia.w) >> 4;
             if ((kFeat & SF_WRAP) && frame != pf_id) {  // (po, pd) = the ray in this primitive's frame; consecutive items mostly share it
@@ -727,9 +751,10 @@ RT_HD void trav_stream(const SceneT<Mem, kFeat>& sc, const Path& path, Trav& tr)
                 pf_id = frame;
             }
             float t;
-            if (prim_hit_t(sc, ia, ib, po, pd, path, frame, 0u, kNear, tr.best_t, t)) {
+            uint32_t face = 0u;
+            if (prim_hit_t(sc, ia, ib, po, pd, path, frame, 0u, kNear, tr.best_t, t, face)) {
                 tr.best_t = t;  // nearest = rec.t (lib.rs:42) / t_range.end = h.t (bvh.rs:98-100, object.rs:404-406)
-                tr.best = i;
+                tr.best = i | (face << 28);
             }
             i += 1u;
         } else if (kind == IT_BBOX) {  // Aabb::hit  aabb.rs:18-29
@@ -740,7 +765,7 @@ RT_HD void trav_stream(const SceneT<Mem, kFeat>& sc, const Path& path, Trav& tr)
             const BestHit h = medium_hit(sc, path.rng(), path.bounce(), path.rtime(), i, tr.fo, tr.fd, tr.f_id, tr.f_nops, tr.best_t, tr.best);
             tr.best_t = h.t;
             tr.best = h.item;
-            i += 2u;
+            i = f2u(ia.z);  // past the boundary run
         } else if (kFrames && kind == IT_SET_FRAME) {
             if (kFrames) {
                 tr.f_id = f2u(ia.w) >> 4;
