@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RTIOW_B200_ABI_VERSION 1u
+#define RTIOW_B200_ABI_VERSION 2u
 
 /* The shared library exports these entry points and nothing else. */
 #if defined(__GNUC__)
@@ -64,14 +64,22 @@ enum {
                                  payload=frame                                                         */
     RTIOW_ITEM_RECT = 3,      /* src/object.rs:183-218: a={k,range0.start,range0.end}
                                  b={range1.start,range1.end,-} payload=frame                           */
-    RTIOW_ITEM_MEDIUM = 4,    /* src/object.rs:543-575: a[0]=density, a[1]=bits(medium id),
-                                 payload=frame of the medium; the NEXT item is its boundary primitive
-                                 (not visited on its own)                                              */
-    RTIOW_ITEM_SET_FRAME = 5  /* following BBOX items live in frame `payload`                          */
+    RTIOW_ITEM_MEDIUM = 4,    /* ConstantMedium<O> src/object.rs:533-575: a[0]=density, a[1]=bits(medium id),
+                                 a[2]=bits(index of the item after its boundary), payload=frame of the
+                                 medium.  The items in between are the boundary object O flattened like any
+                                 other object, in the medium's frame: a sphere, the rects of a rect_prism,
+                                 or the BBOX items (skip links inside the run) and primitives of a Bvh.
+                                 They are asked twice, with f32::MIN.. and hit1.t+0.0001.. (object.rs:551-553),
+                                 and not visited on their own.                                          */
+    RTIOW_ITEM_SET_FRAME = 5, /* following BBOX items live in frame `payload`                          */
+    RTIOW_ITEM_PRISM = 6      /* rect_prism(p0, p1, material) src/object.rs:420-473 as one record:
+                                 a=p0 b=p1 payload=frame; defined as its six Rect items in And order
+                                 (z=p1.z, y=p1.y, x=p1.x, then FlipNormals z=p0.z, y=p0.y, x=p0.x).
+                                 Optional: the library fuses such runs of six RECT items itself.       */
 };
 enum {
     RTIOW_FLAG_HAS_OFFSET = 1u, /* SPHERE: innermost Translate folded into b[0..2] (object.rs:267-283) */
-    RTIOW_FLAG_FLIP = 2u,       /* innermost FlipNormals folded in (object.rs:241-253)                 */
+    RTIOW_FLAG_FLIP = 2u,       /* innermost FlipNormals folded in (object.rs:241-253); PRISM: around all six  */
     RTIOW_FLAG_AXIS_SHIFT = 2u, /* RECT: (flags >> 2) & 3 = orthogonal axis 0=X 1=Y 2=Z                */
 };
 typedef struct rtiow_item_t {

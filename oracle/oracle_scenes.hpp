@@ -276,6 +276,30 @@ inline void kitchen_sink(Scene& sc, SmallRng& rng) {
                                                            sc.n_media++)));
 }
 
+// Not in the reference's own scenes, but in its type system: ConstantMedium<O> takes any Object as boundary
+// (object.rs:533-541).  Shirley's Cornell smoke (two rotated rect_prisms full of smoke, wrappers INSIDE the medium)
+// plus a cloud whose boundary is a Bvh of overlapping spheres and prisms, wrapped from outside.
+inline void cornell_smoke(Scene& sc, SmallRng& rng) {
+    sc.world.list = cornell_box();
+    auto& w = sc.world.list;
+    Material skin = diffuse_color(splat(0.73f));  // the boundary's own material is never shaded
+    w.push_back(std::make_unique<ConstantMedium>(
+        translate(Vec3(130.f, 0.f, 65.f), rotate_y(-18.f, rect_prism(Vec3(0.f, 0.f, 0.f), Vec3(165.f, 165.f, 165.f), skin))), 0.01f,
+        Material::isotropic(tex_constant(splat(1.f))), sc.n_media++));
+    w.push_back(std::make_unique<ConstantMedium>(
+        translate(Vec3(265.f, 0.f, 295.f), rotate_y(15.f, rect_prism(Vec3(0.f, 0.f, 0.f), Vec3(165.f, 330.f, 165.f), skin))), 0.01f,
+        Material::isotropic(tex_constant(splat(0.f))), sc.n_media++));
+    std::vector<ObjectBox> cloud;
+    for (int i = 0; i < 6; ++i) cloud.push_back(translate(90.f * rng.gen_vec3(), sphere(45.f, skin)));
+    for (int i = 0; i < 3; ++i) {
+        Vec3 c = 90.f * rng.gen_vec3();
+        cloud.push_back(rect_prism(c, c + Vec3(50.f, 30.f, 40.f), skin));
+    }
+    w.push_back(translate(Vec3(200.f, 360.f, 200.f),
+                          std::make_unique<ConstantMedium>(Bvh::build(std::move(cloud), 0.f, 1.f), 0.02f,
+                                                           Material::isotropic(tex_constant(Vec3(0.9f, 0.5f, 0.2f))), sc.n_media++)));
+}
+
 // Names are shared with the product's host library (rtiow-rust_b200/csrc/host/scenes.cpp), which
 // builds the same scenes from its own code.  top_level_bvh mirrors USE_BVH (main.rs:321,340-351).
 inline std::unique_ptr<Scene> build(const std::string& name, uint32_t nx, uint32_t ny, uint64_t scene_seed,
@@ -311,6 +335,9 @@ inline std::unique_ptr<Scene> build(const std::string& name, uint32_t nx, uint32
         sc->camera = cornell_camera(nx, ny);
     } else if (name == "simple_light") {
         simple_light_scene(*sc, rng);
+        sc->camera = cornell_camera(nx, ny);
+    } else if (name == "cornell_smoke") {
+        cornell_smoke(*sc, rng);
         sc->camera = cornell_camera(nx, ny);
     } else if (name == "kitchen_sink") {
         kitchen_sink(*sc, rng);

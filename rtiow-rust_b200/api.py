@@ -25,7 +25,7 @@ __all__ = ["Camera", "World", "Image", "RtiowError", "build_scene", "par_cast", 
 
 DEFAULT_SEED = 0xDEADBEEF  # src/main.rs:333
 SCENES = ("book1", "book1_head", "cornell", "cornell_empty", "bench_cornell", "final", "motion_test", "volume_test",
-          "simple_light", "kitchen_sink")
+          "simple_light", "kitchen_sink", "cornell_smoke")
 
 
 class RtiowError(RuntimeError):

@@ -293,6 +293,7 @@ struct rtiow_scene {
     bool specialise = true;        // use a kernel compiled for a subset of features when the scene allows (same image)
     uint32_t refill_lanes = 0;     // 0 = automatic
     bool costly_segments = false;  // the scene has wrapper frames on subtrees or constant media
+    bool fuse_prisms = true;       // six-Rect rect_prism runs become one prism record (RTIOW_B200_FUSE_PRISMS=0: keep the rects)
     bool bottom_first = true;      // unit order (RTIOW_B200_UNIT_ORDER=0: top rows first)
     int phase_sync = -1;           // -1 = automatic (RTIOW_B200_PHASE_SYNC, read once at scene_create)
     uint32_t phase_group_env = 0;  // RTIOW_B200_PHASE_GROUP, 0 = automatic
@@ -310,7 +311,7 @@ using rtiow::KernelVariant;
 rtiow_scene::Blob& blob_of(rtiow_scene* s, rtiow::BlobMode mode) {
     rtiow_scene::Blob& B = s->blobs[mode];
     if (!B.built) {
-        B.host = rtiow::build_blob(&s->desc.d, s->uses_perlin, &B.lay, mode);
+        B.host = rtiow::build_blob(&s->desc.d, s->uses_perlin, &B.lay, mode, s->fuse_prisms);
         B.bytes = static_cast<uint32_t>(B.host.size());
         B.built = true;
     }
@@ -579,6 +580,7 @@ int rtiow_b200_scene_create(const rtiow_scene_desc_t* d, int device, rtiow_scene
     if (const char* env = std::getenv("RTIOW_B200_TRAVERSAL")) s->traversal = std::min(2, std::max(0, std::atoi(env)));
     if (const char* env = std::getenv("RTIOW_B200_SPECIALISE")) s->specialise = std::atoi(env) != 0;
     if (const char* env = std::getenv("RTIOW_B200_REFILL_LANES")) s->refill_lanes = static_cast<uint32_t>(std::min(32, std::max(0, std::atoi(env))));
+    if (const char* env = std::getenv("RTIOW_B200_FUSE_PRISMS")) s->fuse_prisms = std::atoi(env) != 0;
     if (const char* env = std::getenv("RTIOW_B200_UNIT_ORDER")) s->bottom_first = std::atoi(env) != 0;
     if (const char* env = std::getenv("RTIOW_B200_PHASE_SYNC")) s->phase_sync = std::max(0, std::atoi(env));
     if (const char* env = std::getenv("RTIOW_B200_PHASE_GROUP")) s->phase_group_env = static_cast<uint32_t>(std::max(1, std::atoi(env)));

@@ -12,9 +12,12 @@
 namespace rtiow {
 
 // Internal item kind (never part of the ABI): a re-indexed Bvh subtree (accel_build.hpp).
-//   a_w = 6 | (skip << 4)   skip = index of the item after the subtree's primitives
+//   a_w = 7 | (skip << 4)   skip = index of the item after the subtree's primitives
 //   a[0] = bits(root node index);  the subtree's primitive items follow, in stream order.
-constexpr uint32_t kItemAccel = 6u;
+constexpr uint32_t kItemAccel = 7u;
+
+inline uint32_t bits_of(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline float float_of(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 
 inline bool ops_prefix(const rtiow_scene_desc_t* d, uint32_t outer, uint32_t inner) {
     // true if frame `outer`'s op list is a prefix of frame `inner`'s
@@ -66,7 +69,7 @@ inline int validate_desc(const rtiow_scene_desc_t* d, bool* has_frames, bool* us
     auto prim_ok = [&](uint32_t i, uint32_t outer_frame) -> const char* {
         const rtiow_item_t& it = d->items[i];
         const uint32_t kind = it.a_w & 15u, frame = it.a_w >> 4;
-        if (kind != RTIOW_ITEM_SPHERE && kind != RTIOW_ITEM_RECT) return "expected a primitive item";
+        if (kind != RTIOW_ITEM_SPHERE && kind != RTIOW_ITEM_RECT && kind != RTIOW_ITEM_PRISM) return "expected a primitive item";
         if (frame >= d->n_frames) return "primitive frame out of range";
         if ((it.b_w & 0x00ffffffu) >= d->n_materials) return "primitive material out of range";
         if (!ops_prefix(d, outer_frame, frame)) return "primitive frame does not extend the enclosing frame";
@@ -86,19 +89,27 @@ inline int validate_desc(const rtiow_scene_desc_t* d, bool* has_frames, bool* us
                 break;
             case RTIOW_ITEM_SPHERE:
             case RTIOW_ITEM_RECT:
+            case RTIOW_ITEM_PRISM:
                 if (const char* m = prim_ok(i, cur)) return bad(m);
                 break;
             case RTIOW_ITEM_MEDIUM: {
                 if (payload >= d->n_frames || !ops_prefix(d, cur, payload)) return bad("medium frame invalid");
                 if ((it.b_w & 0x00ffffffu) >= d->n_materials) return bad("medium material out of range");
-                if (i + 2 >= d->n_items) return bad("medium without boundary item");
-                if (const char* m = prim_ok(i + 1, payload)) return bad(std::string("medium boundary: ") + m);
-                uint32_t mid;
-                std::memcpy(&mid, &it.a[1], 4);
-                if (mid >= 65536u - 16u) return bad("medium id too large");
-                frame_at[i + 1] = cur;
-                is_boundary[i + 1] = 1;
-                ++i;  // boundary item is consumed with the medium
+                const uint32_t run_end = bits_of(it.a[2]);
+                if (run_end <= i + 1 || run_end >= d->n_items) return bad("medium without boundary items (a[2] must hold the index after its boundary run)");
+                if (bits_of(it.a[1]) >= 65536u - 16u) return bad("medium id too large");
+                // the boundary object, flattened in the medium's frame: primitives, and the boxes of a Bvh boundary
+                for (uint32_t j = i + 1; j < run_end; ++j) {
+                    const uint32_t jk = d->items[j].a_w & 15u, jp = d->items[j].a_w >> 4;
+                    if (jk == RTIOW_ITEM_BBOX) {
+                        if (jp <= j || jp > run_end) return bad("medium boundary: BBOX skip link must stay inside the boundary run");
+                    } else if (const char* m = prim_ok(j, payload)) {
+                        return bad(std::string("medium boundary: ") + m);
+                    }
+                    frame_at[j] = cur;
+                    is_boundary[j] = 1;
+                }
+                i = run_end - 1;  // the boundary run is consumed with the medium
                 break;
             }
             case RTIOW_ITEM_SET_FRAME:
@@ -112,7 +123,7 @@ inline int validate_desc(const rtiow_scene_desc_t* d, bool* has_frames, bool* us
     }
     for (uint32_t i = 0; i < d->n_items; ++i) {
         const rtiow_item_t& it = d->items[i];
-        if ((it.a_w & 15u) == RTIOW_ITEM_BBOX) {
+        if ((it.a_w & 15u) == RTIOW_ITEM_BBOX && !is_boundary[i]) {
             const uint32_t tgt = it.a_w >> 4;
             if (frame_at[tgt] != frame_at[i]) return bad("BBOX skip link crosses a frame change");
             if (is_boundary[tgt]) return bad("BBOX skip link lands on a medium boundary item");
@@ -132,7 +143,7 @@ inline uint32_t scene_features(const rtiow_scene_desc_t* d) {
     for (uint32_t i = 0; i < d->n_items; ++i) {
         const uint32_t kind = d->items[i].a_w & 15u, payload = d->items[i].a_w >> 4;
         if (kind == RTIOW_ITEM_SPHERE) f |= 1u | (wrapped(payload) ? 4u : 0u);
-        else if (kind == RTIOW_ITEM_RECT) f |= 2u | (wrapped(payload) ? 4u : 0u);
+        else if (kind == RTIOW_ITEM_RECT || kind == RTIOW_ITEM_PRISM) f |= 2u | (wrapped(payload) ? 4u : 0u);
         else if (kind == RTIOW_ITEM_MEDIUM) f |= 8u | (wrapped(payload) ? 4u : 0u);
         else if (kind == RTIOW_ITEM_SET_FRAME) f |= 4u;
     }
@@ -151,6 +162,7 @@ struct BlobLayout {
     uint32_t off_nodes, off_frames, off_ops, off_mats, off_tex, off_pvecs, off_pperm;
     uint32_t off_fnodes;
     uint32_t n_items, n_nodes, n_accel, accel_depth;
+    uint32_t n_prisms;  // rect_prism records, fused from six Rect items each or supplied as RTIOW_ITEM_PRISM
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -161,6 +173,77 @@ struct BlobLayout {
 // own leaf boxes.  Everything else is copied, with skip links remapped.
 // ---------------------------------------------------------------------------------------------
 namespace blob_detail {
+
+// ---------------------------------------------------------------------------------------------
+// rect_prism (src/object.rs:420-473) arrives as the six Rect items of its And tree.  Six consecutive
+// items that are exactly that — same frame and material, axes z, y, x, z, y, x, the first three at
+// p1 and the last three (with the opposite FlipNormals state) at p0, ranges equal bit for bit — are
+// replaced by ONE prism record {p0, p1}, which the device evaluates as the same six Rect::hit calls
+// in the same order (path_logic.cuh prism_hit_t): same image, a sixth of the item loads and of the
+// shared-memory footprint (the final scene's 400 boxes: 77 KB -> 13 KB).
+// ---------------------------------------------------------------------------------------------
+inline bool same_bits(float a, float b) { return bits_of(a) == bits_of(b); }
+
+inline bool is_prism_run(const rtiow_item_t* it, rtiow_item_t* fused) {
+    static const uint32_t axes[6] = {2u, 1u, 0u, 2u, 1u, 0u};
+    const uint32_t frame = it[0].a_w >> 4, mat = it[0].b_w & 0x00ffffffu;
+    const bool flip0 = ((it[0].b_w >> 24) & RTIOW_FLAG_FLIP) != 0;
+    for (int f = 0; f < 6; ++f) {
+        const uint32_t flags = it[f].b_w >> 24;
+        if ((it[f].a_w & 15u) != RTIOW_ITEM_RECT || (it[f].a_w >> 4) != frame || (it[f].b_w & 0x00ffffffu) != mat) return false;
+        if (((flags >> 2) & 3u) != axes[f] || (flags & ~(RTIOW_FLAG_FLIP | (3u << 2))) != 0u) return false;
+        if (((flags & RTIOW_FLAG_FLIP) != 0) != (f < 3 ? flip0 : !flip0)) return false;
+    }
+    // item = {k, r0.start, r0.end} {r1.start, r1.end}; z faces: r0 = x, r1 = y; y faces: r0 = x, r1 = z; x faces: r0 = y, r1 = z
+    const float p0x = it[0].a[1], p1x = it[0].a[2], p0y = it[0].b[0], p1y = it[0].b[1], p1z = it[0].a[0], p0z = it[3].a[0];
+    const float want[6][5] = {{p1z, p0x, p1x, p0y, p1y}, {p1y, p0x, p1x, p0z, p1z}, {p1x, p0y, p1y, p0z, p1z},
+                              {p0z, p0x, p1x, p0y, p1y}, {p0y, p0x, p1x, p0z, p1z}, {p0x, p0y, p1y, p0z, p1z}};
+    for (int f = 0; f < 6; ++f) {
+        const float have[5] = {it[f].a[0], it[f].a[1], it[f].a[2], it[f].b[0], it[f].b[1]};
+        for (int k = 0; k < 5; ++k)
+            if (!same_bits(have[k], want[f][k])) return false;
+    }
+    *fused = rtiow_item_t{};
+    fused->a[0] = p0x; fused->a[1] = p0y; fused->a[2] = p0z;
+    fused->b[0] = p1x; fused->b[1] = p1y; fused->b[2] = p1z;
+    fused->a_w = RTIOW_ITEM_PRISM | (frame << 4);
+    fused->b_w = mat | ((flip0 ? static_cast<uint32_t>(RTIOW_FLAG_FLIP) : 0u) << 24);
+    return true;
+}
+
+// Returns the stream with every such run fused, links (BBOX skip, medium run end) remapped.
+inline std::vector<rtiow_item_t> fuse_prisms(const rtiow_item_t* items, uint32_t n) {
+    std::vector<char> is_target(static_cast<size_t>(n) + 1, 0);  // an item some link jumps to
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t kind = items[i].a_w & 15u;
+        if (kind == RTIOW_ITEM_BBOX) is_target[std::min(items[i].a_w >> 4, n)] = 1;
+        else if (kind == RTIOW_ITEM_MEDIUM) is_target[std::min(bits_of(items[i].a[2]), n)] = 1;
+    }
+    std::vector<rtiow_item_t> out;
+    out.reserve(n);
+    std::vector<uint32_t> new_index(static_cast<size_t>(n) + 1, 0);
+    for (uint32_t i = 0; i < n;) {
+        rtiow_item_t fused;
+        bool ok = i + 6 <= n && (items[i].a_w & 15u) == RTIOW_ITEM_RECT;
+        for (uint32_t k = 1; ok && k < 6; ++k) ok = !is_target[i + k];  // nothing may jump into the middle of the six
+        if (ok && is_prism_run(items + i, &fused)) {
+            for (uint32_t k = 0; k < 6; ++k) new_index[i + k] = static_cast<uint32_t>(out.size());
+            out.push_back(fused);
+            i += 6;
+        } else {
+            new_index[i] = static_cast<uint32_t>(out.size());
+            out.push_back(items[i]);
+            i += 1;
+        }
+    }
+    new_index[n] = static_cast<uint32_t>(out.size());
+    for (rtiow_item_t& it : out) {
+        const uint32_t kind = it.a_w & 15u;
+        if (kind == RTIOW_ITEM_BBOX) it.a_w = RTIOW_ITEM_BBOX | (new_index[std::min(it.a_w >> 4, n)] << 4);
+        else if (kind == RTIOW_ITEM_MEDIUM) it.a[2] = float_of(new_index[std::min(bits_of(it.a[2]), n)]);
+    }
+    return out;
+}
 
 struct Compactor {
     const rtiow_scene_desc_t* d;
@@ -190,7 +273,7 @@ struct Compactor {
             return j == s;
         }
         for (uint32_t j = i + 1; j < s; ++j)
-            if (kind(j) != RTIOW_ITEM_SPHERE && kind(j) != RTIOW_ITEM_RECT) return false;
+            if (kind(j) != RTIOW_ITEM_SPHERE && kind(j) != RTIOW_ITEM_RECT && kind(j) != RTIOW_ITEM_PRISM) return false;
         if (s - (i + 1) > kMaxLeafItems) return false;
         leaves->push_back(RawLeaf{i, i + 1, s});
         return true;
@@ -239,10 +322,18 @@ struct Compactor {
                 } else {  // improperly nested skip link (validated to be forward): cannot happen for streams
                     odd_nesting = true;  // produced by the flatteners; keep semantics by disabling compaction
                 }
-            } else if (k == RTIOW_ITEM_MEDIUM) {
+            } else if (k == RTIOW_ITEM_MEDIUM) {  // the medium and its boundary run, as they are (inner skip links shifted)
+                const uint32_t run_end = bits_of(d->items[i].a[2]);
+                const size_t at = out.size();
                 out.push_back(d->items[i]);
-                out.push_back(d->items[i + 1]);
-                i += 2;
+                const uint32_t delta = static_cast<uint32_t>(out.size()) - (i + 1u);  // modulo 2^32: may be "negative"
+                for (uint32_t j = i + 1; j < run_end; ++j) {
+                    rtiow_item_t it = d->items[j];
+                    if ((it.a_w & 15u) == RTIOW_ITEM_BBOX) it.a_w = RTIOW_ITEM_BBOX | (((it.a_w >> 4) + delta) << 4);
+                    out.push_back(it);
+                }
+                out[at].a[2] = float_of(static_cast<uint32_t>(out.size()));
+                i = run_end;
             } else {
                 out.push_back(d->items[i]);
                 i += 1;
@@ -256,9 +347,17 @@ struct Compactor {
 // items | accel nodes | frames | ops | materials | textures | perlin vecs (float4) | perlin perms;
 // every section starts on a 128-byte boundary so the whole blob can be moved with 128 B-granular
 // TMA bulk copies.
-inline std::vector<unsigned char> build_blob(const rtiow_scene_desc_t* d, bool uses_perlin, BlobLayout* lay,
-                                             BlobMode mode = kBlobFast) {
+inline std::vector<unsigned char> build_blob(const rtiow_scene_desc_t* d_in, bool uses_perlin, BlobLayout* lay,
+                                             BlobMode mode = kBlobFast, bool fuse_rect_prisms = true) {
     const bool enable_accel = mode != kBlobReferenceOrder;
+    rtiow_scene_desc_t fused_desc = *d_in;
+    std::vector<rtiow_item_t> fused_items;
+    if (fuse_rect_prisms) {
+        fused_items = blob_detail::fuse_prisms(d_in->items, d_in->n_items);
+        fused_desc.items = fused_items.data();
+        fused_desc.n_items = static_cast<uint32_t>(fused_items.size());
+    }
+    const rtiow_scene_desc_t* d = &fused_desc;
     std::vector<unsigned char> blob;
     auto align_up = [](size_t v) { return (v + 127u) / 128u * 128u; };
     auto append = [&](const void* src, size_t bytes) -> uint32_t {
@@ -275,6 +374,8 @@ inline std::vector<unsigned char> build_blob(const rtiow_scene_desc_t* d, bool u
     }
     append(cp.out.data(), sizeof(rtiow_item_t) * cp.out.size());
     lay->n_items = static_cast<uint32_t>(cp.out.size());
+    lay->n_prisms = 0;
+    for (const rtiow_item_t& it : cp.out) lay->n_prisms += (it.a_w & 15u) == RTIOW_ITEM_PRISM ? 1u : 0u;
     if (mode == kBlobFast) {
         std::vector<FastNode> fast;
         fast.reserve(cp.nodes.size());

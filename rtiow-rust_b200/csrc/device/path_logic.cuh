@@ -269,17 +269,36 @@ RT_HD bool rect_hit_t(V3 o, V3 d, uint32_t axis, float4 ia, float4 ib, float t_l
 // in the tree's visiting order — z = p1.z, y = p1.y, x = p1.x, then the FlipNormals faces z = p0.z, y = p0.y,
 // x = p0.x — each with the arithmetic of rect_hit_axis and the range's end shrunk to the last accepted hit
 // (`hit1.or(hit0)`: the last accepted face wins).  `face` = its position in that order.
-RT_HD bool prism_hit_t(V3 o, V3 d, float4 ia, float4 ib, float t_lo, float t_hi, float& t_out, uint32_t& face) {
-    bool hit = false;
+#ifndef RT_PRISM_INLINE
+#define RT_PRISM_INLINE 0
+#endif
+#if RT_PRISM_INLINE
+#define RT_PRISM_FN RT_HD
+#else
+#define RT_PRISM_FN static RT_HD_NOINLINE  // one copy: the general kernel's code must stay inside the instruction cache
+#endif
+struct PrismHit {
     float t;
-    if (rect_hit_axis(o.z, d.z, o.x, d.x, o.y, d.y, make_float4(ib.z, ia.x, ib.x, 0.f), make_float4(ia.y, ib.y, 0.f, 0.f), t_lo, t_hi, t)) { t_hi = t; face = 0u; hit = true; }
-    if (rect_hit_axis(o.y, d.y, o.x, d.x, o.z, d.z, make_float4(ib.y, ia.x, ib.x, 0.f), make_float4(ia.z, ib.z, 0.f, 0.f), t_lo, t_hi, t)) { t_hi = t; face = 1u; hit = true; }
-    if (rect_hit_axis(o.x, d.x, o.y, d.y, o.z, d.z, make_float4(ib.x, ia.y, ib.y, 0.f), make_float4(ia.z, ib.z, 0.f, 0.f), t_lo, t_hi, t)) { t_hi = t; face = 2u; hit = true; }
-    if (rect_hit_axis(o.z, d.z, o.x, d.x, o.y, d.y, make_float4(ia.z, ia.x, ib.x, 0.f), make_float4(ia.y, ib.y, 0.f, 0.f), t_lo, t_hi, t)) { t_hi = t; face = 3u; hit = true; }
-    if (rect_hit_axis(o.y, d.y, o.x, d.x, o.z, d.z, make_float4(ia.y, ia.x, ib.x, 0.f), make_float4(ia.z, ib.z, 0.f, 0.f), t_lo, t_hi, t)) { t_hi = t; face = 4u; hit = true; }
-    if (rect_hit_axis(o.x, d.x, o.y, d.y, o.z, d.z, make_float4(ia.x, ia.y, ib.y, 0.f), make_float4(ia.z, ib.z, 0.f, 0.f), t_lo, t_hi, t)) { t_hi = t; face = 5u; hit = true; }
-    t_out = t_hi;
-    return hit;
+    uint32_t face;  // 0xffffffff: miss
+};
+RT_PRISM_FN PrismHit prism_hit(V3 o, V3 d, float4 ia, float4 ib, float t_lo, float t_hi);
+RT_HD bool prism_hit_t(V3 o, V3 d, float4 ia, float4 ib, float t_lo, float t_hi, float& t_out, uint32_t& face) {
+    const PrismHit h = prism_hit(o, d, ia, ib, t_lo, t_hi);
+    if (h.face == 0xffffffffu) return false;
+    t_out = h.t;
+    face = h.face;
+    return true;
+}
+RT_PRISM_FN PrismHit prism_hit(V3 o, V3 d, float4 ia, float4 ib, float t_lo, float t_hi) {
+    uint32_t face = 0xffffffffu;
+    float t;
+    if (rect_hit_axis(o.z, d.z, o.x, d.x, o.y, d.y, make_float4(ib.z, ia.x, ib.x, 0.f), make_float4(ia.y, ib.y, 0.f, 0.f), t_lo, t_hi, t)) { t_hi = t; face = 0u; }
+    if (rect_hit_axis(o.y, d.y, o.x, d.x, o.z, d.z, make_float4(ib.y, ia.x, ib.x, 0.f), make_float4(ia.z, ib.z, 0.f, 0.f), t_lo, t_hi, t)) { t_hi = t; face = 1u; }
+    if (rect_hit_axis(o.x, d.x, o.y, d.y, o.z, d.z, make_float4(ib.x, ia.y, ib.y, 0.f), make_float4(ia.z, ib.z, 0.f, 0.f), t_lo, t_hi, t)) { t_hi = t; face = 2u; }
+    if (rect_hit_axis(o.z, d.z, o.x, d.x, o.y, d.y, make_float4(ia.z, ia.x, ib.x, 0.f), make_float4(ia.y, ib.y, 0.f, 0.f), t_lo, t_hi, t)) { t_hi = t; face = 3u; }
+    if (rect_hit_axis(o.y, d.y, o.x, d.x, o.z, d.z, make_float4(ia.y, ia.x, ib.x, 0.f), make_float4(ia.z, ib.z, 0.f, 0.f), t_lo, t_hi, t)) { t_hi = t; face = 4u; }
+    if (rect_hit_axis(o.x, d.x, o.y, d.y, o.z, d.z, make_float4(ia.x, ia.y, ib.y, 0.f), make_float4(ia.z, ib.z, 0.f, 0.f), t_lo, t_hi, t)) { t_hi = t; face = 5u; }
+    return PrismHit{t_hi, face};
 }
 
 // Any primitive item against a ray (o, d) that is already in frame `cur_frame` (whose chain has
@@ -437,6 +456,7 @@ RT_HD void generate_camera_ray(const KParams& P, PathState& st, uint32_t x, uint
 // Aabb::hit (aabb.rs:18-29) with the ray's 1/d hoisted (the same value at every node).  Returns
 // `end > start`; `start` is the entry parameter clamped to NEAR.
 // ------------------------------------------------------------------------------------------------
+RT_HD bool slab_test_from(float4 mn, float4 mx, V3 fo, V3 inv, float t_start, float t_end);
 RT_HD bool slab_test(float4 mn, float4 mx, V3 fo, V3 inv, float t_end, float& start) {
     const float ax = (mn.x - fo.x) * inv.x, ay = (mn.y - fo.y) * inv.y, az = (mn.z - fo.z) * inv.z;
     const float bx = (mx.x - fo.x) * inv.x, by = (mx.y - fo.y) * inv.y, bz = (mx.z - fo.z) * inv.z;
@@ -444,6 +464,19 @@ RT_HD bool slab_test(float4 mn, float4 mx, V3 fo, V3 inv, float t_end, float& st
     const float n0y = inv.y < 0.f ? by : ay, n1y = inv.y < 0.f ? ay : by;
     const float n0z = inv.z < 0.f ? bz : az, n1z = inv.z < 0.f ? az : bz;
     start = rt_max(kNear, rt_max(rt_max(n0x, n0y), n0z));
+    const float end = rt_min(t_end, rt_min(rt_min(n1x, n1y), n1z));
+    return end > start;
+}
+
+// The same test with the caller's t_range.start (a Bvh used as a ConstantMedium boundary is asked with
+// f32::MIN.. and hit1.t + 0.0001.., object.rs:551-553).
+RT_HD bool slab_test_from(float4 mn, float4 mx, V3 fo, V3 inv, float t_start, float t_end) {
+    const float ax = (mn.x - fo.x) * inv.x, ay = (mn.y - fo.y) * inv.y, az = (mn.z - fo.z) * inv.z;
+    const float bx = (mx.x - fo.x) * inv.x, by = (mx.y - fo.y) * inv.y, bz = (mx.z - fo.z) * inv.z;
+    const float n0x = inv.x < 0.f ? bx : ax, n1x = inv.x < 0.f ? ax : bx;
+    const float n0y = inv.y < 0.f ? by : ay, n1y = inv.y < 0.f ? ay : by;
+    const float n0z = inv.z < 0.f ? bz : az, n1z = inv.z < 0.f ? az : bz;
+    const float start = rt_max(t_start, rt_max(rt_max(n0x, n0y), n0z));
     const float end = rt_min(t_end, rt_min(rt_min(n1x, n1y), n1z));
     return end > start;
 }
@@ -676,7 +709,34 @@ RT_HD_NOINLINE bool prim_hit_outline(const SceneT<Mem, kFeat> sc, float4 ia, flo
     return prim_hit_t(sc, ia, ib, o, d, TimeOnlyView{time}, cur_frame, cur_nops, t_lo, t_hi, t_out, face);
 }
 
-// ConstantMedium::hit (object.rs:543-575); item i is the medium, item i+1 its boundary primitive.
+// ConstantMedium::hit (object.rs:543-575).  Item i is the medium; items [i + 1, run_end) are its boundary object
+// flattened like any other object — primitives (one sphere, the rects of a rect_prism ...) and, for a Bvh boundary,
+// BBOX items with skip links — in the medium's frame; run_end = bits(a[2]) of the medium item.
+//
+// boundary.hit(ray, t_lo..t_hi): the run in the reference's visiting order with a shrinking t_range.end
+// (Bvh::hit bvh.rs:85-120, And::hit object.rs:396-410).  Only t is needed (object.rs:551-556).
+template <class Mem, uint32_t kFeat>
+RT_HD_NOINLINE bool boundary_hit(const SceneT<Mem, kFeat> sc, uint32_t first, uint32_t run_end, V3 mo, V3 md, float time,
+                                 uint32_t mframe, uint32_t m_nops, float t_lo, float t_hi, float& t_out) {
+    bool found = false;
+    const V3 inv = mk(1.f / md.x, 1.f / md.y, 1.f / md.z);  // aabb.rs:19
+    for (uint32_t j = first; j < run_end;) {
+        const float4 ja = sc.item_a(j), jb = sc.item_b(j);
+        if ((f2u(ja.w) & 15u) == IT_BBOX) {
+            j = slab_test_from(ja, jb, mo, inv, t_lo, t_hi) ? j + 1u : (f2u(ja.w) >> 4);
+        } else {
+            float t;
+            if (prim_hit_outline(sc, ja, jb, mo, md, time, mframe, m_nops, t_lo, t_hi, t)) {
+                t_hi = t;
+                found = true;
+            }
+            j += 1u;
+        }
+    }
+    t_out = t_hi;
+    return found;
+}
+
 struct BestHit {
     float t;
     uint32_t item;
@@ -695,10 +755,10 @@ RT_HD_NOINLINE BestHit medium_hit(const SceneT<Mem, kFeat> sc, Rng rng, uint32_t
         md = r.d;
         m_nops = fr.y;
     }
-    const float4 ba = sc.item_a(i + 1u), bb = sc.item_b(i + 1u);
+    const uint32_t run_end = f2u(ia.z);
     float t1, t2;
-    if (prim_hit_outline(sc, ba, bb, mo, md, time, mframe, m_nops, kF32Min, kF32Max, t1) &&
-        prim_hit_outline(sc, ba, bb, mo, md, time, mframe, m_nops, t1 + 0.0001f, kF32Max, t2)) {
+    if (boundary_hit(sc, i + 1u, run_end, mo, md, time, mframe, m_nops, kF32Min, kF32Max, t1) &&
+        boundary_hit(sc, i + 1u, run_end, mo, md, time, mframe, m_nops, t1 + 0.0001f, kF32Max, t2)) {
         t1 = rt_max(t1, kNear);
         t2 = rt_min(t2, best_t);
         if (!(t1 >= t2)) {
@@ -833,6 +893,8 @@ RT_HD bool shade_and_scatter(const SceneT<Mem, kFeat>& sc, const KParams& P, Pat
         return true;
     }
     // ---- rebuild the HitRecord of the winning item (object.rs:61-71) --------------------------
+    const uint32_t face = best >> 28;  // which rect of a prism (0 for everything else)
+    best &= kItemMask;
     const float4 ia = sc.item_a(best), ib = sc.item_b(best);
     const uint32_t kind = f2u(ia.w) & 15u;
     const uint32_t flags = f2u(ib.w) >> 24;
@@ -853,11 +915,13 @@ RT_HD bool shade_and_scatter(const SceneT<Mem, kFeat>& sc, const KParams& P, Pat
         n = p / ia.x;          // object.rs:104
         if (flags & FL_FLIP) n = -n;
         if (flags & FL_HAS_OFFSET) p = p + mk(ib.x, ib.y, ib.z);
-    } else if ((kFeat & SF_RECT) && (!(kFeat & SF_MEDIUM) || kind == IT_RECT)) {
+    } else if ((kFeat & SF_RECT) && (!(kFeat & SF_MEDIUM) || kind == IT_RECT || kind == IT_PRISM)) {
         p = lo + best_t * ld;  // object.rs:209
-        const uint32_t axis = (flags >> 2) & 3u;
+        // a prism's faces in And order: z, y, x at p1, then the three FlipNormals faces at p0 (object.rs:420-473)
+        const bool prism = kind == IT_PRISM;
+        const uint32_t axis = prism ? 2u - (face >= 3u ? face - 3u : face) : ((flags >> 2) & 3u);
         n = mk(axis == 0 ? 1.f : 0.f, axis == 1 ? 1.f : 0.f, axis == 2 ? 1.f : 0.f);
-        if (flags & FL_FLIP) n = -n;
+        if (((flags & FL_FLIP) != 0u) != (prism && face >= 3u)) n = -n;
     } else {                   // medium  object.rs:565-570
         p = lo + best_t * ld;
         n = mk(1.f, 0.f, 0.f);

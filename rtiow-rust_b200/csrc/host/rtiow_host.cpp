@@ -271,7 +271,6 @@ void SceneBuilder::emit_rect(int axis, Range r0, Range r1, float k, const materi
 }
 
 size_t SceneBuilder::begin_bbox(const Aabb& box) {
-    if (medium_depth_) throw std::runtime_error("ConstantMedium boundary must be a (wrapped) Sphere or Rect, not a Bvh");
     rtiow_item_t it{};
     it.a[0] = box.min.x; it.a[1] = box.min.y; it.a[2] = box.min.z;
     it.b[0] = box.max.x; it.b[1] = box.max.y; it.b[2] = box.max.z;
@@ -284,7 +283,15 @@ void SceneBuilder::end_bbox(size_t token) {
 }
 
 void SceneBuilder::begin_subtree() {
-    if (medium_depth_) throw std::runtime_error("ConstantMedium boundary must be a (wrapped) Sphere or Rect, not a Bvh");
+    if (medium_depth_) {
+        // a Bvh as ConstantMedium boundary: its boxes are tested in the medium's frame, so no wrapper may sit between
+        // the medium and the Bvh (wrap the medium instead: Translate{ConstantMedium{Bvh}} renders the same)
+        if (chain_.size() != prefix_stack_.back())
+            throw std::runtime_error("a Bvh used as ConstantMedium boundary must not be wrapped inside the medium; wrap the ConstantMedium instead");
+        frame_stack_.push_back(cur_frame_);
+        prefix_stack_.push_back(chain_.size());
+        return;
+    }
     frame_stack_.push_back(cur_frame_);
     if (chain_.size() != prefix_stack_.back()) {  // wrappers since the enclosing frame: boxes live in a new frame
         const uint32_t f = intern_frame(chain_.size());
@@ -308,7 +315,7 @@ void SceneBuilder::end_subtree() {
 }
 
 void SceneBuilder::begin_medium(float density, const material::Material& m, uint32_t medium_id) {
-    if (medium_depth_) throw std::runtime_error("ConstantMedium boundary must be a (wrapped) Sphere or Rect, not a ConstantMedium");
+    if (medium_depth_) throw std::runtime_error("a ConstantMedium inside a ConstantMedium boundary is not supported");
     rtiow_item_t it{};
     it.a[0] = density;
     it.a[1] = as_float(medium_id);
@@ -322,8 +329,8 @@ void SceneBuilder::begin_medium(float density, const material::Material& m, uint
 void SceneBuilder::end_medium() {
     --medium_depth_;
     prefix_stack_.pop_back();
-    if (items_.size() != medium_item_ + 2)
-        throw std::runtime_error("ConstantMedium boundary must flatten to exactly one primitive (a wrapped Sphere or Rect)");
+    if (items_.size() == medium_item_ + 1) throw std::runtime_error("ConstantMedium boundary flattened to nothing");
+    items_[medium_item_].a[2] = as_float(static_cast<uint32_t>(items_.size()));  // index after the boundary run
 }
 
 void SceneBuilder::set_background(uint32_t kind, Vec3 c0, Vec3 c1) {

@@ -152,6 +152,34 @@ std::vector<Box> kitchen_sink(SmallRng& rng, Range exposure, uint32_t& n_media) 
 
 }  // namespace
 
+std::vector<Box> cornell_box();
+
+namespace {
+// ConstantMedium<O> with boundaries other than one primitive (object.rs:533-541 takes any Object): Shirley's Cornell
+// smoke — two rotated rect_prisms, the wrappers inside the medium — and a cloud bounded by a Bvh, wrapped from outside.
+std::vector<Box> cornell_smoke(SmallRng& rng, Range exposure, uint32_t& n_media) {
+    std::vector<Box> w = cornell_box();
+    const Material skin = diffuse_color(Vec3::from(0.73f));
+    w.push_back(std::make_unique<object::ConstantMedium>(
+        translate(Vec3(130.f, 0.f, 65.f), object::rotate_y(-18.f, object::rect_prism(Vec3(0.f, 0.f, 0.f), Vec3(165.f, 165.f, 165.f), skin))),
+        0.01f, Material::Isotropic(texture::constant(Vec3::from(1.f))), n_media++));
+    w.push_back(std::make_unique<object::ConstantMedium>(
+        translate(Vec3(265.f, 0.f, 295.f), object::rotate_y(15.f, object::rect_prism(Vec3(0.f, 0.f, 0.f), Vec3(165.f, 330.f, 165.f), skin))),
+        0.01f, Material::Isotropic(texture::constant(Vec3::from(0.f))), n_media++));
+    std::vector<Box> cloud;
+    for (int i = 0; i < 6; ++i) cloud.push_back(translate(90.f * rng.gen_vec3(), sphere(45.f, skin)));
+    for (int i = 0; i < 3; ++i) {
+        const Vec3 c = 90.f * rng.gen_vec3();
+        cloud.push_back(object::rect_prism(c, c + Vec3(50.f, 30.f, 40.f), skin));
+    }
+    w.push_back(translate(Vec3(200.f, 360.f, 200.f),
+                          std::make_unique<object::ConstantMedium>(bvh::from_scene(std::move(cloud), exposure), 0.02f,
+                                                                   Material::Isotropic(texture::constant(Vec3(0.9f, 0.5f, 0.2f))),
+                                                                   n_media++)));
+    return w;
+}
+}  // namespace
+
 std::vector<Box> cornell_box() {  // lib.rs:103-166
     const Material red = diffuse_color(Vec3(0.65f, 0.05f, 0.05f));
     const Material white = diffuse_color(Vec3::from(0.73f));
@@ -221,6 +249,9 @@ BuiltScene build_scene(const std::string& name, size_t nx, size_t ny, uint64_t s
             world.push_back(translate(off, sphere(20.f, diffuse_color(Vec3::from(0.3f)))));
         }
         world.push_back(flip(sphere(1000.f, Material::DiffuseLight(texture::constant(Vec3::from(0.1f)), 1.f))));
+        out.camera = cornell_camera(nx, ny, out.exposure);
+    } else if (name == "cornell_smoke") {
+        world = cornell_smoke(rng, out.exposure, n_media);
         out.camera = cornell_camera(nx, ny, out.exposure);
     } else if (name == "kitchen_sink") {
         world = kitchen_sink(rng, out.exposure, n_media);

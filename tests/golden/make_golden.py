@@ -20,6 +20,8 @@ CASES = [  # name, nx, ny, ns, top_level_bvh
     ("final", 24, 24, 6, False), ("final", 24, 24, 6, True), ("motion_test", 24, 24, 4, False),
     ("volume_test", 24, 24, 4, False), ("simple_light", 24, 24, 3, True), ("kitchen_sink", 32, 24, 6, False),
     ("kitchen_sink", 32, 24, 6, True),
+    # round 2: ConstantMedium with rect_prism and Bvh boundaries (object.rs:533-541 takes any Object)
+    ("cornell_smoke", 32, 32, 6, False), ("cornell_smoke", 32, 32, 6, True),
 ]
 SEED = 0xDEADBEEF
 
@@ -31,7 +33,12 @@ def main():
         key = f"{name}|{nx}|{ny}|{ns}|{int(bvh)}"
         out[key] = img
         out[key + "|segments"] = np.array([cnt["segments"]], np.uint64)
-    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_v1.npz"), **out)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_v1.npz")
+    if os.path.exists(path):   # fixtures are append-only: an existing case must come out bit-identical
+        old = np.load(path)
+        for k in old.files:
+            assert k in out and np.array_equal(old[k].view(np.uint8), out[k].view(np.uint8)), f"golden case {k} changed"
+    np.savez_compressed(path, **out)
     print(f"wrote {len(CASES)} cases")
 
 

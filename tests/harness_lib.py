@@ -28,25 +28,25 @@ def lib():
     return _lib
 
 
-def trace_rays(world, rays, accel):
+def trace_rays(world, rays, accel, fuse_prisms=True):
     """hit_top for explicit rays [n, 7] = (origin, direction, time) -> uint32 [n, 2] = (winner id, bits of t)."""
     rays = np.ascontiguousarray(rays, np.float32)
     out = np.zeros((rays.shape[0], 2), np.uint32)
-    rc = lib().harness_trace_rays(C.cast(world.desc, C.c_void_p), rays.shape[0], rays.ctypes.data, out.ctypes.data, int(accel))
+    rc = lib().harness_trace_rays(C.cast(world.desc, C.c_void_p), rays.shape[0], rays.ctypes.data, out.ctypes.data, int(accel) | (0 if fuse_prisms else 0x200))
     if rc:
         raise RuntimeError(f"harness_trace_rays failed: {rc}")
     return out
 
 
 def render(world, camera, nx, ny, ns, seed=0xDEADBEEF, rows=None, want_samples=False, accel=True, layout=None, row_step=1,
-           row_band=1, lean=False):
+           row_band=1, lean=False, fuse_prisms=True):
     """rows=(begin, end): bands of row_band rows starting at begin, begin + row_step, ... clipped to end."""
     r0, r1 = rows if rows is not None else (0, ny)
     n_rows = sum(min(row_band, r1 - b) for b in range(r0, r1, row_step))
     img = np.zeros((n_rows, nx, 3), np.float32)
     smp = np.zeros((n_rows, nx, ns, 4), np.float32) if want_samples else None
     rc = lib().harness_render(C.cast(world.desc, C.c_void_p), C.byref(camera.rec), nx, ny, ns, seed, r0, r1,
-                              img.ctypes.data, smp.ctypes.data if want_samples else None, int(accel) | (0x100 if lean else 0),
+                              img.ctypes.data, smp.ctypes.data if want_samples else None, int(accel) | (0x100 if lean else 0) | (0 if fuse_prisms else 0x200),
                               layout.ctypes.data if layout is not None else None, row_step, row_band)
     if rc:
         raise RuntimeError(f"harness_render failed: {rc}")

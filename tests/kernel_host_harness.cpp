@@ -14,7 +14,9 @@
 
 // accel = 1: the re-indexed (SAH, ordered) traversal with conservative inner box tests that the device
 // uses by default; 2: the same tree with the reference's exact box test at every node; 0: the plain
-// reference-order stream.
+// reference-order stream.  Bit 9 (0x200) of the callers' `accel` argument: keep rect_prisms as their six Rect items
+// instead of fusing them into prism records (scene_blob.hpp fuse_prisms).
+static bool g_fuse_prisms = true;
 template <uint32_t kFeat>
 static int harness_render_impl(const rtiow_scene_desc_t* desc, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny,
                                uint32_t ns, uint64_t seed, uint32_t row_begin, uint32_t row_end, float* out_rgb,
@@ -24,8 +26,8 @@ static int harness_render_impl(const rtiow_scene_desc_t* desc, const rtiow_camer
     std::string msg;
     if (int rc = validate_desc(desc, &has_frames, &uses_perlin, &msg)) return rc;
     BlobLayout lay{};
-    const std::vector<unsigned char> blob = build_blob(desc, uses_perlin, &lay, accel == 1 ? kBlobFast : (accel == 2 ? kBlobExact : kBlobReferenceOrder));
-    if (layout_out) { layout_out[0] = lay.n_items; layout_out[1] = lay.n_nodes; layout_out[2] = lay.n_accel; layout_out[3] = lay.accel_depth; }
+    const std::vector<unsigned char> blob = build_blob(desc, uses_perlin, &lay, accel == 1 ? kBlobFast : (accel == 2 ? kBlobExact : kBlobReferenceOrder), g_fuse_prisms);
+    if (layout_out) { layout_out[0] = lay.n_items; layout_out[1] = lay.n_nodes; layout_out[2] = lay.n_accel; layout_out[3] = lay.accel_depth; layout_out[5] = lay.n_prisms; layout_out[6] = static_cast<uint32_t>(blob.size()); }
     KParams P{};
     P.blob = blob.data();
     P.blob_bytes = static_cast<uint32_t>(blob.size());
@@ -81,6 +83,7 @@ extern "C" __attribute__((visibility("default"))) int harness_render(const rtiow
                               uint32_t ns, uint64_t seed, uint32_t row_begin, uint32_t row_end, float* out_rgb,
                               float* out_samples, int accel, uint32_t* layout_out, uint32_t row_step, uint32_t row_band) {
     const bool specialise = (accel & 0x100) != 0;
+    g_fuse_prisms = (accel & 0x200) == 0;
     accel &= 0xff;
     uint32_t profile = 0;
     if (specialise) {
@@ -105,11 +108,13 @@ extern "C" __attribute__((visibility("default"))) int harness_render(const rtiow
 extern "C" __attribute__((visibility("default"))) int harness_trace_rays(const rtiow_scene_desc_t* desc, uint32_t n, const float* rays,
                                                                          uint32_t* out, int accel) {
     using namespace rtiow;
+    g_fuse_prisms = (accel & 0x200) == 0;
+    accel &= 0xff;
     bool has_frames = false, uses_perlin = false;
     std::string msg;
     if (int rc = validate_desc(desc, &has_frames, &uses_perlin, &msg)) return rc;
     BlobLayout lay{};
-    const std::vector<unsigned char> blob = build_blob(desc, uses_perlin, &lay, accel == 1 ? kBlobFast : (accel == 2 ? kBlobExact : kBlobReferenceOrder));
+    const std::vector<unsigned char> blob = build_blob(desc, uses_perlin, &lay, accel == 1 ? kBlobFast : (accel == 2 ? kBlobExact : kBlobReferenceOrder), g_fuse_prisms);
     KParams P{};
     P.blob = blob.data();
     P.off_nodes = lay.off_nodes; P.off_frames = lay.off_frames; P.off_ops = lay.off_ops; P.off_mats = lay.off_mats; P.off_tex = lay.off_tex;
@@ -130,9 +135,10 @@ extern "C" __attribute__((visibility("default"))) int harness_trace_rays(const r
         // identify the winner by its primitive record (item numbering differs between blobs)
         uint32_t id = 0xffffffffu;
         if (best != kNoHit) {
-            const float4 a = sc.item_a(best), b = sc.item_b(best);
+            const float4 a = sc.item_a(best & kItemMask), b = sc.item_b(best & kItemMask);
             uint32_t h = 2166136261u;
-            const uint32_t w[8] = {f2u(a.x), f2u(a.y), f2u(a.z), f2u(a.w) & 15u, f2u(b.x), f2u(b.y), f2u(b.z), f2u(b.w)};
+            const bool medium = (f2u(a.w) & 15u) == IT_MEDIUM;  // a[2] of a medium is an item index: differs between blobs
+            const uint32_t w[8] = {f2u(a.x), f2u(a.y), medium ? 0u : f2u(a.z), f2u(a.w) & 15u, f2u(b.x), f2u(b.y), f2u(b.z), f2u(b.w) | (best & ~kItemMask)};
             for (uint32_t k = 0; k < 8; ++k) h = (h ^ w[k]) * 16777619u;
             id = h & 0x7fffffffu;
         }
