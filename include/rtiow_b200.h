@@ -196,6 +196,11 @@ typedef struct rtiow_stats_t {
 typedef struct rtiow_scene rtiow_scene_t;
 
 RTIOW_API int rtiow_b200_abi_version(void);
+/* Which arithmetic this build of the library uses: "parity: ..." (the default build: every f32 operation as the
+ * reference does it, results bit-identical to the oracle) or "fast: ..." (make FAST=1: fused multiply-add and
+ * approximate division/sqrt; same algorithm and random numbers, image within a tolerance — mean |delta| <= 1e-3
+ * linear, >= 99.5 % of 8-bit PPM values within +-1 at >= 50 spp). */
+RTIOW_API const char* rtiow_b200_build_flavour(void);
 RTIOW_API const char* rtiow_b200_last_error(void);
 
 /* Checks `desc` exactly as rtiow_b200_scene_create does, without touching a GPU. */

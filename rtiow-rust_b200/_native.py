@@ -13,6 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # RTIOW_B200_BUILD_DIR selects another in-tree build (`make OUT=_build_x`): same-box A/B timing of two kernels
 BUILD_DIR = os.path.join(_HERE, os.environ.get("RTIOW_B200_BUILD_DIR", "_build"))
 ABI_LIB = os.path.join(BUILD_DIR, "librtiow_b200.so")
+# the tolerance build of the same library (make FAST=1): FMA contraction, approximate division / square root
+FAST_ABI_LIB = os.path.join(_HERE, "_build_fast", "librtiow_b200.so")
 HOST_LIB = os.path.join(BUILD_DIR, "librtiow_host.so")
 
 RTIOW_OK, ERR_INVALID_ARG, ERR_INVALID_SCENE, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = range(6)
@@ -64,13 +66,13 @@ class Stats(C.Structure):
 
 
 # every symbol include/rtiow_b200.h declares
-ABI_SYMBOLS = ("rtiow_b200_abi_version", "rtiow_b200_last_error", "rtiow_b200_scene_validate",
+ABI_SYMBOLS = ("rtiow_b200_abi_version", "rtiow_b200_build_flavour", "rtiow_b200_last_error", "rtiow_b200_scene_validate",
                "rtiow_b200_scene_create", "rtiow_b200_scene_destroy", "rtiow_b200_release_cached_memory", "rtiow_b200_render", "rtiow_b200_render_rows",
                "rtiow_b200_render_rows_device", "rtiow_b200_render_rows_strided_device", "rtiow_b200_render_samples", "rtiow_b200_ppm_quantise",
                "rtiow_b200_ppm_quantise_device", "rtiow_b200_render_ppm",
                "rtiow_b200_get_stats", "rtiow_b200_set_tuning", "rtiow_b200_set_traversal", "rtiow_b200_set_specialisation")
 
-_abi = None
+_abi = {}
 _host = None
 
 
@@ -80,34 +82,47 @@ def _missing(path):
         f"(or `make -C {_HERE}`) — there is no Python/CPU fallback for the render path.")
 
 
-def abi():
-    global _abi
-    if _abi is None:
-        if not os.path.exists(ABI_LIB):
-            raise _missing(ABI_LIB)
-        L = C.CDLL(ABI_LIB, mode=C.RTLD_GLOBAL)
-        u32, u64, vp = C.c_uint32, C.c_uint64, C.c_void_p
-        L.rtiow_b200_abi_version.restype = C.c_int
-        L.rtiow_b200_last_error.restype = C.c_char_p
-        L.rtiow_b200_scene_validate.argtypes = [C.POINTER(SceneDesc)]
-        L.rtiow_b200_scene_create.argtypes = [C.POINTER(SceneDesc), C.c_int, C.POINTER(vp)]
-        L.rtiow_b200_scene_destroy.argtypes = [vp]
-        L.rtiow_b200_scene_destroy.restype = None
-        L.rtiow_b200_release_cached_memory.restype = None
-        L.rtiow_b200_render.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, vp]
-        L.rtiow_b200_render_rows.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, u32, u32, vp]
-        L.rtiow_b200_render_rows_device.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, u32, u32, vp, vp]
-        L.rtiow_b200_render_rows_strided_device.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, u32, u32, u32, u32, vp, vp]
-        L.rtiow_b200_render_samples.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, u32, u32, vp]
-        L.rtiow_b200_ppm_quantise.argtypes = [vp, vp, C.c_size_t, vp]
-        L.rtiow_b200_ppm_quantise_device.argtypes = [vp, vp, C.c_size_t, vp, vp]
-        L.rtiow_b200_render_ppm.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, vp]
-        L.rtiow_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
-        L.rtiow_b200_set_tuning.argtypes = [vp, u32, u32, u32, C.c_int]
-        L.rtiow_b200_set_traversal.argtypes = [vp, C.c_int]
-        L.rtiow_b200_set_specialisation.argtypes = [vp, C.c_int]
-        _abi = L
-    return _abi
+def _declare(L):
+    u32, u64, vp = C.c_uint32, C.c_uint64, C.c_void_p
+    L.rtiow_b200_abi_version.restype = C.c_int
+    L.rtiow_b200_build_flavour.restype = C.c_char_p
+    L.rtiow_b200_last_error.restype = C.c_char_p
+    L.rtiow_b200_scene_validate.argtypes = [C.POINTER(SceneDesc)]
+    L.rtiow_b200_scene_create.argtypes = [C.POINTER(SceneDesc), C.c_int, C.POINTER(vp)]
+    L.rtiow_b200_scene_destroy.argtypes = [vp]
+    L.rtiow_b200_scene_destroy.restype = None
+    L.rtiow_b200_release_cached_memory.restype = None
+    L.rtiow_b200_render.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, vp]
+    L.rtiow_b200_render_rows.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, u32, u32, vp]
+    L.rtiow_b200_render_rows_device.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, u32, u32, vp, vp]
+    L.rtiow_b200_render_rows_strided_device.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, u32, u32, u32, u32, vp, vp]
+    L.rtiow_b200_render_samples.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, u32, u32, vp]
+    L.rtiow_b200_ppm_quantise.argtypes = [vp, vp, C.c_size_t, vp]
+    L.rtiow_b200_ppm_quantise_device.argtypes = [vp, vp, C.c_size_t, vp, vp]
+    L.rtiow_b200_render_ppm.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, vp]
+    L.rtiow_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.rtiow_b200_set_tuning.argtypes = [vp, u32, u32, u32, C.c_int]
+    L.rtiow_b200_set_traversal.argtypes = [vp, C.c_int]
+    L.rtiow_b200_set_specialisation.argtypes = [vp, C.c_int]
+    return L
+
+
+def abi(flavour="parity"):
+    """The C ABI library.  flavour "parity" (default; what every parity test pins) or "fast" (the tolerance build,
+    `make FAST=1`): the same entry points, loaded side by side (hidden internals, -Bsymbolic)."""
+    if flavour not in _abi:
+        if flavour == "parity":
+            if not os.path.exists(ABI_LIB):
+                raise _missing(ABI_LIB)
+            _abi[flavour] = _declare(C.CDLL(ABI_LIB, mode=C.RTLD_GLOBAL))
+        elif flavour == "fast":
+            if not os.path.exists(FAST_ABI_LIB):
+                raise _missing(FAST_ABI_LIB)
+            _abi[flavour] = _declare(C.CDLL(FAST_ABI_LIB))
+            assert _abi[flavour].rtiow_b200_build_flavour().startswith(b"fast")
+        else:
+            raise ValueError(f"unknown library flavour {flavour!r}")
+    return _abi[flavour]
 
 
 def host():

@@ -34,9 +34,9 @@ class RtiowError(RuntimeError):
         self.code = code
 
 
-def _check(rc):
+def _check(rc, lib=None):
     if rc != 0:
-        raise RtiowError(rc, N.abi().rtiow_b200_last_error().decode())
+        raise RtiowError(rc, (lib or N.abi()).rtiow_b200_last_error().decode())
 
 
 class Camera:
@@ -78,10 +78,15 @@ class World:
     """`impl World` (src/lib.rs:23-55): a flattened scene (list or Bvh top level) plus, lazily, its
     device-resident copy.  Obtain one from build_scene()."""
 
-    def __init__(self, host_handle, name):
+    def __init__(self, host_handle, name, flavour="parity"):
         self._h = host_handle
         self.name = name
+        self.flavour = flavour      # which build of the device library renders it: "parity" (default) or "fast"
         self._gpu = {}
+
+    @property
+    def lib(self):
+        return N.abi(self.flavour)
 
     def __del__(self):
         try:
@@ -91,7 +96,7 @@ class World:
 
     def close(self):
         for h in list(self._gpu.values()):
-            N.abi().rtiow_b200_scene_destroy(h)
+            self.lib.rtiow_b200_scene_destroy(h)
         self._gpu = {}
         if self._h:
             N.host().rtiow_host_scene_free(self._h)
@@ -105,7 +110,7 @@ class World:
         return N.host().rtiow_host_scene_desc(self._h)
 
     def validate(self):
-        _check(N.abi().rtiow_b200_scene_validate(self.desc))
+        _check(self.lib.rtiow_b200_scene_validate(self.desc), self.lib)
 
     def items(self):
         d = self.desc.contents
@@ -124,27 +129,27 @@ class World:
         """rtiow_b200_scene_create: upload to `device` (once) and return the handle."""
         if device not in self._gpu:
             h = C.c_void_p()
-            _check(N.abi().rtiow_b200_scene_create(self.desc, device, C.byref(h)))
+            _check(self.lib.rtiow_b200_scene_create(self.desc, device, C.byref(h)), self.lib)
             self._gpu[device] = h
         return self._gpu[device]
 
     def upload_fresh(self, device=0):
         """Drop and re-create the device copy (used by the end-to-end timing: H2D inside the timed region)."""
         if device in self._gpu:
-            N.abi().rtiow_b200_scene_destroy(self._gpu.pop(device))
+            self.lib.rtiow_b200_scene_destroy(self._gpu.pop(device))
         return self.gpu(device)
 
     def set_tuning(self, device=0, cta_threads=0, ctas_per_sm=0, staging_mib=0, force_global=False):
-        _check(N.abi().rtiow_b200_set_tuning(self.gpu(device), cta_threads, ctas_per_sm, staging_mib, int(force_global)))
+        _check(self.lib.rtiow_b200_set_tuning(self.gpu(device), cta_threads, ctas_per_sm, staging_mib, int(force_global)), self.lib)
 
     def set_specialisation(self, enable=True, device=0):
         """False forces the general megakernel even if the scene qualifies for a specialised one.  Same image."""
-        _check(N.abi().rtiow_b200_set_specialisation(self.gpu(device), int(bool(enable))))
+        _check(self.lib.rtiow_b200_set_specialisation(self.gpu(device), int(bool(enable))), self.lib)
 
     def set_traversal(self, mode, device=0):
         """0 = re-indexed Bvh subtrees, conservative inner box test (default); 1 = the reference's own visiting
         order; 2 = re-indexed with the reference's box test at every node.  Same image every way."""
-        _check(N.abi().rtiow_b200_set_traversal(self.gpu(device), int(mode)))
+        _check(self.lib.rtiow_b200_set_traversal(self.gpu(device), int(mode)), self.lib)
 
     def scene_bytes(self, device=0):
         """Bytes of the device image of the scene the last render used (uploaded by scene_create)."""
@@ -152,17 +157,18 @@ class World:
 
     def stats(self, device=0):
         st = N.Stats()
-        _check(N.abi().rtiow_b200_get_stats(self.gpu(device), C.byref(st)))
+        _check(self.lib.rtiow_b200_get_stats(self.gpu(device), C.byref(st)), self.lib)
         return {f: getattr(st, f) for f, _ in st._fields_}
 
 
-def build_scene(name, nx, ny, scene_seed=DEFAULT_SEED, use_bvh=True):
+def build_scene(name, nx, ny, scene_seed=DEFAULT_SEED, use_bvh=True, flavour="parity"):
     """The reference's scene functions by name (src/lib.rs:103-193,237-319; src/main.rs:10-319;
-    benches/scene.rs).  Returns (world, camera).  use_bvh mirrors USE_BVH (src/main.rs:321)."""
+    benches/scene.rs).  Returns (world, camera).  use_bvh mirrors USE_BVH (src/main.rs:321).
+    flavour="fast" renders it with the tolerance build of the device library (make FAST=1)."""
     h = N.host().rtiow_host_scene_build(name.encode(), nx, ny, scene_seed, int(use_bvh))
     if not h:
         raise RuntimeError(N.host().rtiow_host_last_error().decode())
-    world = World(h, name)
+    world = World(h, name, flavour)
     cam = N.CameraRec()
     C.memmove(C.byref(cam), N.host().rtiow_host_scene_camera(h), C.sizeof(cam))
     return world, Camera(cam)
@@ -173,8 +179,8 @@ def par_cast(nx, ny, ns, camera, world, seed=DEFAULT_SEED, device=0, rows=None):
     `rows=(begin, end)` renders only those output rows (row 0 = top)."""
     r0, r1 = rows if rows is not None else (0, ny)
     out = np.empty((r1 - r0, nx, 3), np.float32)
-    _check(N.abi().rtiow_b200_render_rows(world.gpu(device), C.byref(camera.rec), nx, ny, ns, seed, r0, r1,
-                                          out.ctypes.data))
+    _check(world.lib.rtiow_b200_render_rows(world.gpu(device), C.byref(camera.rec), nx, ny, ns, seed, r0, r1,
+                                          out.ctypes.data), world.lib)
     return Image(out)
 
 
@@ -188,8 +194,8 @@ def render_samples(nx, ny, ns, camera, world, seed=DEFAULT_SEED, device=0, rows=
     """Per-sample radiance before the fold: [rows, nx, ns, 4] = r, g, b, path segments."""
     r0, r1 = rows if rows is not None else (0, ny)
     out = np.empty((r1 - r0, nx, ns, 4), np.float32)
-    _check(N.abi().rtiow_b200_render_samples(world.gpu(device), C.byref(camera.rec), nx, ny, ns, seed, r0, r1,
-                                             out.ctypes.data))
+    _check(world.lib.rtiow_b200_render_samples(world.gpu(device), C.byref(camera.rec), nx, ny, ns, seed, r0, r1,
+                                             out.ctypes.data), world.lib)
     return out
 
 
@@ -202,15 +208,15 @@ def render_rows_device(nx, ny, ns, camera, world, out_tensor, rows, seed=DEFAULT
     assert out_tensor.numel() >= sum(min(row_band, r1 - b) for b in range(r0, r1, row_step)) * nx * 3
     dev = out_tensor.device.index or 0
     s = stream if stream is not None else torch.cuda.current_stream(dev)
-    _check(N.abi().rtiow_b200_render_rows_strided_device(world.gpu(dev), C.byref(camera.rec), nx, ny, ns, seed, r0, r1, row_step, row_band,
-                                                         C.c_void_p(out_tensor.data_ptr()), C.c_void_p(s.cuda_stream)))
+    _check(world.lib.rtiow_b200_render_rows_strided_device(world.gpu(dev), C.byref(camera.rec), nx, ny, ns, seed, r0, r1, row_step, row_band,
+                                                         C.c_void_p(out_tensor.data_ptr()), C.c_void_p(s.cuda_stream)), world.lib)
 
 
 def ppm_bytes(image, world=None, device=0):
     """print_ppm's quantiser (sqrt, then to_u8; src/lib.rs:344-361) on the device -> uint8 [ny, nx, 3]."""
     rgb = np.ascontiguousarray(image.rgb if isinstance(image, Image) else image, np.float32)
     out = np.empty(rgb.shape, np.uint8)
-    _check(N.abi().rtiow_b200_ppm_quantise(world.gpu(device), rgb.ctypes.data, rgb.size, out.ctypes.data))
+    _check(world.lib.rtiow_b200_ppm_quantise(world.gpu(device), rgb.ctypes.data, rgb.size, out.ctypes.data), world.lib)
     return out
 
 
@@ -222,8 +228,8 @@ def ppm_bytes_device(frame, world, stream=None):
     dev = frame.device.index or 0
     out = torch.empty(frame.shape, dtype=torch.uint8, device=frame.device)
     s = stream if stream is not None else torch.cuda.current_stream(dev)
-    _check(N.abi().rtiow_b200_ppm_quantise_device(world.gpu(dev), C.c_void_p(frame.data_ptr()), frame.numel(),
-                                                  C.c_void_p(out.data_ptr()), C.c_void_p(s.cuda_stream)))
+    _check(world.lib.rtiow_b200_ppm_quantise_device(world.gpu(dev), C.c_void_p(frame.data_ptr()), frame.numel(),
+                                                  C.c_void_p(out.data_ptr()), C.c_void_p(s.cuda_stream)), world.lib)
     return out
 
 
@@ -231,7 +237,7 @@ def par_cast_ppm(nx, ny, ns, camera, world, seed=DEFAULT_SEED, device=0):
     """par_cast + print_ppm's quantiser in one device-side call (rtiow_b200_render_ppm): uint8 [ny, nx, 3], the numbers
     print_ppm writes (src/lib.rs:346-360); a quarter of the float frame's bytes come back over PCIe."""
     out = np.empty((ny, nx, 3), np.uint8)
-    _check(N.abi().rtiow_b200_render_ppm(world.gpu(device), C.byref(camera.rec), nx, ny, ns, seed, out.ctypes.data))
+    _check(world.lib.rtiow_b200_render_ppm(world.gpu(device), C.byref(camera.rec), nx, ny, ns, seed, out.ctypes.data), world.lib)
     return out
 
 

@@ -520,6 +520,13 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
 extern "C" {
 
 int rtiow_b200_abi_version(void) { return static_cast<int>(RTIOW_B200_ABI_VERSION); }
+const char* rtiow_b200_build_flavour(void) {
+#if RT_FAST_MATH
+    return "fast: FMA contraction, approximate division / square root / transcendentals; within tolerance of the reference arithmetic, not bit-exact";
+#else
+    return "parity: no FMA contraction, IEEE division and square root, fixed transcendentals; decision-for-decision the reference's f32 arithmetic";
+#endif
+}
 const char* rtiow_b200_last_error(void) { return g_err.c_str(); }
 
 int rtiow_b200_scene_validate(const rtiow_scene_desc_t* d) {

@@ -757,8 +757,16 @@ RT_HD_NOINLINE BestHit medium_hit(const SceneT<Mem, kFeat> sc, Rng rng, uint32_t
     }
     const uint32_t run_end = f2u(ia.z);
     float t1, t2;
-    if (boundary_hit(sc, i + 1u, run_end, mo, md, time, mframe, m_nops, kF32Min, kF32Max, t1) &&
-        boundary_hit(sc, i + 1u, run_end, mo, md, time, mframe, m_nops, t1 + 0.0001f, kF32Max, t2)) {
+    bool both;
+    const float4 ba = sc.item_a(i + 1u), bb = sc.item_b(i + 1u);
+    if (run_end == i + 2u && (f2u(ba.w) & 15u) != IT_BBOX) {  // the usual boundary, one primitive (a sphere of fog): no run to walk
+        both = prim_hit_outline(sc, ba, bb, mo, md, time, mframe, m_nops, kF32Min, kF32Max, t1) &&
+               prim_hit_outline(sc, ba, bb, mo, md, time, mframe, m_nops, t1 + 0.0001f, kF32Max, t2);
+    } else {
+        both = boundary_hit(sc, i + 1u, run_end, mo, md, time, mframe, m_nops, kF32Min, kF32Max, t1) &&
+               boundary_hit(sc, i + 1u, run_end, mo, md, time, mframe, m_nops, t1 + 0.0001f, kF32Max, t2);
+    }
+    if (both) {
         t1 = rt_max(t1, kNear);
         t2 = rt_min(t2, best_t);
         if (!(t1 >= t2)) {

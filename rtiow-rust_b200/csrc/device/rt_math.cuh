@@ -7,6 +7,9 @@
 // /root/reference/src.
 #pragma once
 #include <cstdint>
+#ifndef RT_FAST_MATH
+#define RT_FAST_MATH 0  // 1: the tolerance build (Makefile FAST=1); everything below describes the parity build
+#endif
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
 #define RT_HD __host__ __device__ __forceinline__
@@ -152,6 +155,9 @@ RT_HD double ull2d(unsigned long long u) {
 // f32::ln of ConstantMedium::hit (object.rs:562).  fdlibm-style: x = 2^k * m, m in [sqrt(1/2), sqrt(2)),
 // log(m) from the s = f/(2+f) series.
 RT_HD float ln_f32(float xf) {
+#if defined(__CUDA_ARCH__) && RT_FAST_MATH
+    return __logf(xf);  // tolerance build only
+#endif
     if (xf != xf) return xf;
     if (xf < 0.f) return u2f(0x7fc00000u);
     if (xf == 0.f) return u2f(0xff800000u);
@@ -180,6 +186,10 @@ RT_HD float ln_f32(float xf) {
 
 // f32::powf(x, 5.) of schlick (material.rs:145): x^5 in double, rounded once.
 RT_HD float pow5_f32(float xf) {
+#if defined(__CUDA_ARCH__) && RT_FAST_MATH
+    const float x2 = xf * xf;
+    return x2 * x2 * xf;  // tolerance build only
+#endif
     double d = static_cast<double>(xf);
     double d2 = d * d;
     double d4 = d2 * d2;
@@ -189,6 +199,9 @@ RT_HD float pow5_f32(float xf) {
 // f32::sin of the checker texture (texture.rs:14): reduce by pi/2 in double, then the classic
 // short odd/even polynomials in double.
 RT_HD float sin_f32(float xf) {
+#if defined(__CUDA_ARCH__) && RT_FAST_MATH
+    return sinf(xf);  // tolerance build only (not __sinf: the checker's argument 10 * p is not small)
+#endif
     if (xf != xf || fabsf(xf) == u2f(0x7f800000u)) return u2f(0x7fc00000u);
     if (fabsf(xf) < 0.000244140625f) return xf;
     double x = static_cast<double>(xf);

@@ -135,7 +135,7 @@ def par_cast_e2e(nx, ny, ns, camera, world, bufs, host_out, seed=api.DEFAULT_SEE
     dev = bufs.frame.device.index or 0
     world.upload_fresh(dev)
     if sh.world_size == 1:
-        api._check(N.abi().rtiow_b200_render(world.gpu(dev), C.byref(camera.rec), nx, ny, ns, seed, host_out.ctypes.data))
+        api._check(world.lib.rtiow_b200_render(world.gpu(dev), C.byref(camera.rec), nx, ny, ns, seed, host_out.ctypes.data), world.lib)
         return world.scene_bytes(dev) + C.sizeof(N.CameraRec), host_out.nbytes
     render_sharded_device(nx, ny, ns, camera, world, bufs, seed=seed)
     h2d = world.scene_bytes(dev) + C.sizeof(N.CameraRec)

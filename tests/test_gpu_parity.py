@@ -307,6 +307,52 @@ def test_print_ppm_bytes_on_device(oracle):
     assert api.ppm_bytes_device(edge, world).cpu().tolist() == [0, 255, 255, 0, 0, 255, 127, 0]
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# The tolerance build (make FAST=1 -> _build_fast/librtiow_b200.so): FMA contraction, approximate division and
+# square root.  Same algorithm, same random numbers, NOT bit-exact.  SURVEY §8c rung R2: against the oracle on the same
+# seeds, mean |delta| of the linear image <= 1e-3 and >= 99.5 % of the 8-bit PPM channel values within +-1 at >= 50 spp.
+# ---------------------------------------------------------------------------------------------------------------
+R2_MEAN_ABS_TOL = 1e-3
+R2_PPM_WITHIN_1 = 0.995
+
+
+@pytest.mark.parametrize("name,bvh,nx,ny,ns", [("book1", True, 400, 200, 50), ("cornell", False, 160, 160, 64),
+                                               ("final", False, 160, 160, 64), ("kitchen_sink", True, 160, 120, 64),
+                                               ("cornell_smoke", False, 128, 128, 64)])
+def test_fast_build_within_tolerance_of_the_oracle(oracle, name, bvh, nx, ny, ns):
+    fast_world, cam = R.build_scene(name, nx, ny, use_bvh=bvh, flavour="fast")
+    assert N.abi("fast").rtiow_b200_build_flavour().startswith(b"fast") and N.abi().rtiow_b200_build_flavour().startswith(b"parity")
+    got = R.par_cast(nx, ny, ns, cam, fast_world).rgb
+    want, _, _ = oracle.Scene(name, nx, ny, top_level_bvh=bvh).render(ns, nthreads=NT)
+    assert np.isfinite(got).all()
+    mean_abs = float(np.abs(got.astype(np.float64) - want.astype(np.float64)).mean())
+    assert mean_abs <= R2_MEAN_ABS_TOL, (name, mean_abs)
+    q_fast = api.ppm_bytes(got, fast_world).astype(np.int32)
+    q_want = oracle.ppm_quantise(want)
+    within1 = float((np.abs(q_fast - q_want) <= 1).mean())
+    assert within1 >= R2_PPM_WITHIN_1, (name, within1)
+    # and the parity build, in the same process, still gives the oracle's bits
+    world, _ = R.build_scene(name, nx, ny, use_bvh=bvh)
+    assert n_diff(R.par_cast(nx, ny, ns, cam, world).rgb, want) == 0
+    frac_equal = float((got.view(np.uint32) == want.view(np.uint32)).mean())
+    print(f"fast build {name}: mean|d| {mean_abs:.3e}, PPM within 1: {within1:.5f}, floats bit-equal to the oracle: {frac_equal:.3f}")
+
+
+def test_fast_build_agrees_statistically_with_other_seeds(oracle):
+    """Rung R3 for the tolerance build: an oracle render with another seed is another sample of the same estimator."""
+    nx, ny, ns = 96, 64, 64
+    world, cam = R.build_scene("book1", nx, ny, flavour="fast")
+    smp = api.render_samples(nx, ny, ns, cam, world, seed=777)[..., :3].astype(np.float64)
+    gpu_mean = smp.mean(axis=2)
+    se = smp.std(axis=2, ddof=1) / np.sqrt(ns)
+    want, _, _ = oracle.Scene("book1", nx, ny).render(ns, seed=12345, nthreads=NT)
+    ok = se > 1e-6
+    z = (want.astype(np.float64) - gpu_mean)[ok] / (np.sqrt(2.0) * se[ok])
+    q50, q90 = np.percentile(np.abs(z), [50, 90])
+    assert 0.55 < q50 < 0.8 and 1.4 < q90 < 2.0, (q50, q90)
+    assert abs((want.astype(np.float64) - gpu_mean).mean()) < 3e-3
+
+
 def test_philox_core_matches_curand(tmp_path):
     """The RNG core of the render path (rt_math.cuh philox4x32_10) against NVIDIA's independent implementation
     (curand_Philox4x32_10) on 4 M (counter, key) pairs: pins the generator to something that is not ours."""

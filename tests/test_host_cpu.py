@@ -25,13 +25,17 @@ def test_abi_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "rtiow_b200.h")).read()
     declared = set(re.findall(r"\b(rtiow_b200_\w+)\s*\(", header))
     assert declared == set(N.ABI_SYMBOLS)
-    lib = N.abi()
-    for sym in declared:
-        assert getattr(lib, sym) is not None
-    assert lib.rtiow_b200_abi_version() == 2
-    nm = subprocess.run(["nm", "-D", "--defined-only", N.ABI_LIB], capture_output=True, text=True).stdout
-    for sym in declared:
-        assert re.search(rf"\bT {sym}\b", nm), sym
+    for flavour, path in (("parity", N.ABI_LIB), ("fast", N.FAST_ABI_LIB)):   # the default build and the tolerance build (make FAST=1)
+        lib = N.abi(flavour)
+        for sym in declared:
+            assert getattr(lib, sym) is not None
+        assert lib.rtiow_b200_abi_version() == 2
+        assert lib.rtiow_b200_build_flavour().decode().startswith(flavour)
+        nm = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True).stdout
+        for sym in declared:
+            assert re.search(rf"\bT {sym}\b", nm), sym
+        exported = set(re.findall(r"\bT (\w+)", nm))
+        assert exported == declared, exported ^ declared       # nothing else leaks out of the library
 
 
 def test_abi_struct_sizes_match_header():
