@@ -239,6 +239,45 @@ RTIOW_API int rtiow_b200_render_rows_strided_device(rtiow_scene_t* scene, const 
                                           uint32_t ns, uint64_t seed, uint32_t row_begin, uint32_t row_end,
                                           uint32_t row_step, uint32_t band_rows, float* d_out_rows, void* cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Several GPUs.  par_cast parallelises over scanlines (src/lib.rs:324-332); here the frame is cut into
+ * bands of `band_rows` scanlines dealt round-robin to the GPUs (GPU g: bands g, g + G, ...), every GPU
+ * renders its bands with its own copy of the scene, and the kernel that finishes a pixel (the
+ * in-order sample fold) stores it straight into the frame of every GPU that wants it, through NVLink
+ * peer pointers, at the row's final position: the framebuffer exchange is fused into the fold, there is
+ * no all-gather and no de-interleave pass behind it.  Every row is bit-identical to the same row of
+ * rtiow_b200_render, for any number of GPUs.
+ *
+ * One host process: rtiow_b200_render_multi is par_cast over `ngpus` scene handles (one per device,
+ * created from the same descriptor).  One process per GPU (torchrun, MPI): each rank creates a peer
+ * frame, the opaque handles are exchanged by whatever transport the host has, and
+ * rtiow_b200_render_rows_peers leaves the whole image in every rank's frame.
+ * ------------------------------------------------------------------------------------------- */
+RTIOW_API int rtiow_b200_render_multi(rtiow_scene_t* const* scenes, int ngpus, const rtiow_camera_t* camera, uint32_t nx,
+                                      uint32_t ny, uint32_t ns, uint64_t seed, float* out_rgb);
+
+typedef struct rtiow_peer_frame rtiow_peer_frame_t;
+#define RTIOW_PEER_HANDLE_BYTES 128u
+/* This rank's copy of the ny*nx*3 float frame (+ hand-shake flags) on `device`; n_ranks <= 16. */
+RTIOW_API int rtiow_b200_peer_frame_create(int device, uint32_t nx, uint32_t ny, uint32_t rank, uint32_t n_ranks,
+                                           rtiow_peer_frame_t** out);
+/* RTIOW_PEER_HANDLE_BYTES bytes that let another rank (another process, or this one) map this frame. */
+RTIOW_API int rtiow_b200_peer_frame_export(rtiow_peer_frame_t* frame, uint8_t* handle);
+/* `handles`: the exported handles of all n_ranks ranks, in rank order.  Maps the peers' frames (CUDA IPC across
+ * processes, peer access inside one). */
+RTIOW_API int rtiow_b200_peer_frame_connect(rtiow_peer_frame_t* frame, const uint8_t* handles);
+/* DEVICE pointer to this rank's frame: ny*nx*3 floats, row 0 = top. */
+RTIOW_API int rtiow_b200_peer_frame_ptr(rtiow_peer_frame_t* frame, float** d_frame);
+RTIOW_API void rtiow_b200_peer_frame_destroy(rtiow_peer_frame_t* frame);
+/* This rank's share of par_cast, enqueued on `cuda_stream`: signals "my frame may be overwritten", renders bands
+ * rank, rank + n_ranks, ... , waits for every peer's signal, folds the samples into EVERY rank's frame, signals
+ * "my rows are there" and waits for everybody's.  When the stream reaches the end the frame of this rank holds the
+ * whole image.  All ranks must make the same sequence of calls; a rank that does not arrive within 60 s makes the
+ * next call fail instead of hanging the GPU. */
+RTIOW_API int rtiow_b200_render_rows_peers(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny,
+                                           uint32_t ns, uint64_t seed, uint32_t band_rows, rtiow_peer_frame_t* frame,
+                                           void* cuda_stream);
+
 /* Parity/debug: per-sample radiance before the fold, HOST memory,
  * (row_end-row_begin)*nx*ns*4 floats laid out [row][x][sample]{r,g,b,segments}. */
 RTIOW_API int rtiow_b200_render_samples(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny,

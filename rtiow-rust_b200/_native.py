@@ -14,9 +14,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 BUILD_DIR = os.path.join(_HERE, os.environ.get("RTIOW_B200_BUILD_DIR", "_build"))
 ABI_LIB = os.path.join(BUILD_DIR, "librtiow_b200.so")
 # the tolerance build of the same library (make FAST=1): FMA contraction, approximate division / square root
-FAST_ABI_LIB = os.path.join(_HERE, "_build_fast", "librtiow_b200.so")
+FAST_ABI_LIB = os.path.join(_HERE, os.environ.get("RTIOW_B200_FAST_BUILD_DIR", "_build_fast"), "librtiow_b200.so")
 HOST_LIB = os.path.join(BUILD_DIR, "librtiow_host.so")
 
+PEER_HANDLE_BYTES = 128
 RTIOW_OK, ERR_INVALID_ARG, ERR_INVALID_SCENE, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = range(6)
 
 
@@ -70,6 +71,8 @@ ABI_SYMBOLS = ("rtiow_b200_abi_version", "rtiow_b200_build_flavour", "rtiow_b200
                "rtiow_b200_scene_create", "rtiow_b200_scene_destroy", "rtiow_b200_release_cached_memory", "rtiow_b200_render", "rtiow_b200_render_rows",
                "rtiow_b200_render_rows_device", "rtiow_b200_render_rows_strided_device", "rtiow_b200_render_samples", "rtiow_b200_ppm_quantise",
                "rtiow_b200_ppm_quantise_device", "rtiow_b200_render_ppm",
+               "rtiow_b200_render_multi", "rtiow_b200_peer_frame_create", "rtiow_b200_peer_frame_export", "rtiow_b200_peer_frame_connect",
+               "rtiow_b200_peer_frame_ptr", "rtiow_b200_peer_frame_destroy", "rtiow_b200_render_rows_peers",
                "rtiow_b200_get_stats", "rtiow_b200_set_tuning", "rtiow_b200_set_traversal", "rtiow_b200_set_specialisation")
 
 _abi = {}
@@ -100,6 +103,14 @@ def _declare(L):
     L.rtiow_b200_ppm_quantise.argtypes = [vp, vp, C.c_size_t, vp]
     L.rtiow_b200_ppm_quantise_device.argtypes = [vp, vp, C.c_size_t, vp, vp]
     L.rtiow_b200_render_ppm.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, vp]
+    L.rtiow_b200_render_multi.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(CameraRec), u32, u32, u32, u64, vp]
+    L.rtiow_b200_peer_frame_create.argtypes = [C.c_int, u32, u32, u32, u32, C.POINTER(vp)]
+    L.rtiow_b200_peer_frame_export.argtypes = [vp, vp]
+    L.rtiow_b200_peer_frame_connect.argtypes = [vp, vp]
+    L.rtiow_b200_peer_frame_ptr.argtypes = [vp, C.POINTER(vp)]
+    L.rtiow_b200_peer_frame_destroy.argtypes = [vp]
+    L.rtiow_b200_peer_frame_destroy.restype = None
+    L.rtiow_b200_render_rows_peers.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, u32, vp, vp]
     L.rtiow_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.rtiow_b200_set_tuning.argtypes = [vp, u32, u32, u32, C.c_int]
     L.rtiow_b200_set_traversal.argtypes = [vp, C.c_int]

@@ -20,7 +20,7 @@ import numpy as np
 
 from . import _native as N
 
-__all__ = ["Camera", "World", "Image", "RtiowError", "build_scene", "par_cast", "par_cast_ppm", "cast", "print_ppm", "ppm_bytes", "ppm_bytes_device",
+__all__ = ["Camera", "World", "Image", "RtiowError", "build_scene", "par_cast", "par_cast_multi", "par_cast_ppm", "cast", "print_ppm", "ppm_bytes", "ppm_bytes_device",
            "SCENES", "DEFAULT_SEED"]
 
 DEFAULT_SEED = 0xDEADBEEF  # src/main.rs:333
@@ -181,6 +181,17 @@ def par_cast(nx, ny, ns, camera, world, seed=DEFAULT_SEED, device=0, rows=None):
     out = np.empty((r1 - r0, nx, 3), np.float32)
     _check(world.lib.rtiow_b200_render_rows(world.gpu(device), C.byref(camera.rec), nx, ny, ns, seed, r0, r1,
                                           out.ctypes.data), world.lib)
+    return Image(out)
+
+
+def par_cast_multi(nx, ny, ns, camera, worlds, seed=DEFAULT_SEED):
+    """par_cast over several GPUs from ONE host thread (rtiow_b200_render_multi): `worlds` = the same scene built once per
+    device, in device order 0, 1, ...  Bands of scanlines are dealt round-robin, every GPU's fold stores its rows straight
+    into GPU 0's frame over NVLink, GPU 0 copies the frame out.  Bit-identical to par_cast."""
+    lib = worlds[0].lib
+    handles = (C.c_void_p * len(worlds))(*[w.gpu(i) for i, w in enumerate(worlds)])
+    out = np.empty((ny, nx, 3), np.float32)
+    _check(lib.rtiow_b200_render_multi(handles, len(worlds), C.byref(camera.rec), nx, ny, ns, seed, out.ctypes.data), lib)
     return Image(out)
 
 

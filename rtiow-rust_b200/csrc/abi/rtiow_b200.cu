@@ -2,6 +2,8 @@
 // persistent megakernel launch per sample pass, the sample fold, statistics.
 // No CPU fallback: every entry point fails with RTIOW_ERR_NO_DEVICE / RTIOW_ERR_CUDA if the
 // device path is unavailable.
+#include <unistd.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -194,6 +196,17 @@ cudaError_t kernel_info(const void* fn, int device, int max_smem_optin, int* reg
 
 std::mutex g_ws_mutex;
 std::vector<Workspace*> g_ws_cache;
+
+// rtiow_b200_render_multi keeps the devices' frames between calls of the same shape (at most two shapes)
+struct MultiFrames {
+    uint32_t nx = 0, ny = 0;
+    std::vector<int> devices;
+    std::vector<rtiow_peer_frame_t*> pf;
+    void destroy();
+};
+std::mutex g_multi_mutex;
+std::vector<MultiFrames> g_multi_cache;
+
 constexpr size_t kWsCachePerDevice = 2;
 
 Workspace* ws_acquire(int device, cudaError_t* err) {
@@ -349,10 +362,22 @@ int check_render_args(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, ui
     return RTIOW_OK;
 }
 
-// Enqueue a full render of rows [r0, r1) into device buffer d_out (rgb floats) and/or d_samples.
+// Where a multi-GPU render puts its rows and how it meets its peers (rtiow_b200_render_rows_peers).
+struct PeerTarget {
+    rtiow::FoldDst dst{};          // every rank's frame, rows at their position in the image
+    rtiow::PeerFlags ready{};      // slot [rank] of every rank's "ready" array
+    const unsigned int* my_ready = nullptr;
+    unsigned int epoch = 0;
+    uint32_t n_ranks = 1;
+    unsigned int* timed_out = nullptr;
+};
+constexpr unsigned long long kPeerTimeoutNs = 60ull * 1000ull * 1000ull * 1000ull;
+
+// Enqueue a full render of rows [r0, r1) into device buffer d_out (rgb floats, packed) — or, with `peers`, into
+// every rank's frame at the rows' image positions — and/or d_samples.
 int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny, uint32_t ns, uint64_t seed,
                    uint32_t r0, uint32_t r1, float* d_out, float4* d_samples, cudaStream_t stream, uint32_t step = 1,
-                   uint32_t band = 1) {
+                   uint32_t band = 1, const PeerTarget* peers = nullptr) {
     CK(cudaSetDevice(s->device));
     // bands of `band` rows starting at r0, r0 + step, ..., clipped to r1
     const uint32_t n_full = (r1 - r0) / step, rest = (r1 - r0) - n_full * step;
@@ -487,9 +512,26 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
             CK(cudaGetLastError());
             ++launches;
         }
-        if (d_out) {
+        if (d_out || peers) {
+            rtiow::FoldDst dst{};
+            if (peers) {
+                dst = peers->dst;
+                dst.nx = nx; dst.row_begin = r0; dst.row_step = step; dst.row_band = band;
+                dst.image_rows = 1u;
+                if (pass + 1 == n_pass && peers->n_ranks > 1) {
+                    // the last fold writes into the peers' frames: not before every peer has finished with the previous
+                    // frame (its "ready" for this epoch was enqueued at the start of its call, long ago by now)
+                    rtiow::peer_wait_kernel<<<1, 32, 0, stream>>>(peers->my_ready, peers->n_ranks, peers->epoch, kPeerTimeoutNs,
+                                                                  peers->timed_out);
+                    CK(cudaGetLastError());
+                    ++launches;
+                }
+            } else {
+                dst.p[0] = d_out;
+                dst.n = 1u;
+            }
             rtiow::fold_kernel<<<(npix + 255u) / 256u, 256, 0, stream>>>(
-                P.staging, static_cast<float4*>(W.accum.p), d_out, npix, P.s_count, pass == 0, pass + 1 == n_pass,
+                P.staging, static_cast<float4*>(W.accum.p), dst, npix, P.s_count, pass == 0, pass + 1 == n_pass,
                 static_cast<float>(ns), W.d_segs);
             CK(cudaGetLastError());
             ++launches;
@@ -605,6 +647,11 @@ int rtiow_b200_scene_create(const rtiow_scene_desc_t* d, int device, rtiow_scene
 }
 
 void rtiow_b200_release_cached_memory(void) {
+    {
+        std::lock_guard<std::mutex> lock(g_multi_mutex);
+        for (MultiFrames& c : g_multi_cache) c.destroy();
+        g_multi_cache.clear();
+    }
     std::vector<Workspace*> drop;
     {
         std::lock_guard<std::mutex> lock(g_ws_mutex);
@@ -730,6 +777,268 @@ int rtiow_b200_render_ppm(rtiow_scene_t* s, const rtiow_camera_t* cam, uint32_t 
     CK(W.mark_render_end(W.stream));
     CK(W.copy_to_host(out_rgb8, W.samples.p, n));  // a quarter of the float frame's bytes over PCIe
     return RTIOW_OK;
+}
+
+}  // extern "C"
+
+// One rank's copy of the frame plus its hand-shake flags, in ONE cudaMalloc allocation that the other ranks map
+// (CUDA IPC between processes, peer access inside one): [frame ny*nx*3 f32 | ready[16] u32 | done[16] u32].
+struct rtiow_peer_frame {
+    int device = 0;
+    uint32_t nx = 0, ny = 0, rank = 0, n_ranks = 1;
+    size_t frame_bytes = 0, bytes = 0;
+    unsigned char* base = nullptr;             // my allocation
+    unsigned char* peer_base[rtiow::kMaxFoldDst] = {};  // everybody's (peer_base[rank] == base)
+    bool opened_ipc[rtiow::kMaxFoldDst] = {};
+    bool connected = false;
+    unsigned int epoch = 0;
+    unsigned int* timed_out = nullptr;         // pinned, mapped: the wait kernels raise it, the host reads it without a sync
+    cudaEvent_t done_ev = nullptr;             // single-process multi-GPU: end of this device's part
+
+    float* frame(uint32_t q) const { return reinterpret_cast<float*>(peer_base[q]); }
+    unsigned int* ready(uint32_t q) const { return reinterpret_cast<unsigned int*>(peer_base[q] + frame_bytes); }
+    unsigned int* done(uint32_t q) const { return ready(q) + rtiow::kMaxFoldDst; }
+};
+
+namespace {
+
+struct PeerHandleWire {  // RTIOW_PEER_HANDLE_BYTES on the wire
+    cudaIpcMemHandle_t ipc;   // 64 bytes
+    uint64_t pid;
+    uint64_t ptr;             // valid inside process `pid`
+    uint64_t bytes;
+    int32_t device;
+    uint32_t nx, ny, rank, n_ranks;
+    uint32_t magic;
+};
+static_assert(sizeof(PeerHandleWire) <= RTIOW_PEER_HANDLE_BYTES, "peer handle does not fit");
+constexpr uint32_t kPeerMagic = 0x52543230u;
+
+uint64_t my_pid();
+
+// Renders rank `pf->rank`'s bands of `band` rows into the frames listed in `dst_ranks` (a bit mask) and, if `handshake`,
+// runs the ready / done protocol with all ranks.
+int render_bands(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny, uint32_t ns, uint64_t seed, uint32_t band,
+                 rtiow_peer_frame* pf, uint32_t dst_mask, bool handshake, cudaStream_t stream) {
+    if (!pf->connected && pf->n_ranks > 1) return set_err(RTIOW_ERR_INVALID_ARG, "peer frame is not connected");
+    if (pf->nx != nx || pf->ny != ny) return set_err(RTIOW_ERR_INVALID_ARG, "peer frame has another size");
+    if (s->device != pf->device) return set_err(RTIOW_ERR_INVALID_ARG, "scene and peer frame live on different devices");
+    if (*pf->timed_out) return set_err(RTIOW_ERR_CUDA, "a peer did not arrive within the time-out in an earlier multi-GPU render");
+    CK(cudaSetDevice(s->device));
+    const uint32_t G = pf->n_ranks, r0 = pf->rank * band, step = G * band;
+    PeerTarget T{};
+    T.n_ranks = G;
+    T.epoch = ++pf->epoch;
+    T.timed_out = pf->timed_out;
+    T.my_ready = pf->ready(pf->rank);
+    rtiow::PeerFlags done{};
+    for (uint32_t q = 0; q < G; ++q) {
+        if (dst_mask & (1u << q)) T.dst.p[T.dst.n++] = pf->frame(q);
+        T.ready.p[q] = pf->ready(q);
+        done.p[q] = pf->done(q);
+    }
+    T.ready.n = done.n = G;
+    const bool sync = handshake && G > 1;
+    if (sync) {  // "I am done with the previous frame": peers may overwrite my copy from their next fold on
+        rtiow::peer_signal_kernel<<<1, 32, 0, stream>>>(T.ready, pf->rank, T.epoch);
+        CK(cudaGetLastError());
+    }
+    PeerTarget Tq = T;
+    if (!sync) Tq.n_ranks = 1;  // no wait before the fold
+    if (r0 < ny) {
+        if (int rc = enqueue_render(s, cam, nx, ny, ns, seed, r0, ny, nullptr, nullptr, stream, step, band, &Tq)) return rc;
+    } else if (sync) {  // more ranks than bands: nothing to render, but the protocol still runs
+        rtiow::peer_wait_kernel<<<1, 32, 0, stream>>>(T.my_ready, G, T.epoch, kPeerTimeoutNs, T.timed_out);
+        CK(cudaGetLastError());
+    }
+    if (sync) {  // my rows are in every frame -> tell everybody; the frame is whole once everybody has told me
+        rtiow::peer_signal_kernel<<<1, 32, 0, stream>>>(done, pf->rank, T.epoch);
+        CK(cudaGetLastError());
+        rtiow::peer_wait_kernel<<<1, 32, 0, stream>>>(pf->done(pf->rank), G, T.epoch, kPeerTimeoutNs, T.timed_out);
+        CK(cudaGetLastError());
+        CK(s->ws->mark_render_end(stream));
+    }
+    return RTIOW_OK;
+}
+
+uint64_t my_pid() { return static_cast<uint64_t>(getpid()); }
+
+
+}  // namespace
+
+extern "C" {
+
+int rtiow_b200_peer_frame_create(int device, uint32_t nx, uint32_t ny, uint32_t rank, uint32_t n_ranks, rtiow_peer_frame_t** out) {
+    if (!out) return set_err(RTIOW_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (nx == 0 || ny == 0 || n_ranks == 0 || rank >= n_ranks || n_ranks > static_cast<uint32_t>(rtiow::kMaxFoldDst))
+        return set_err(RTIOW_ERR_INVALID_ARG, "need nx, ny > 0 and rank < n_ranks <= 16");
+    CK(cudaSetDevice(device));
+    auto pf = new rtiow_peer_frame();
+    pf->device = device; pf->nx = nx; pf->ny = ny; pf->rank = rank; pf->n_ranks = n_ranks;
+    pf->frame_bytes = (static_cast<size_t>(nx) * ny * 3 * sizeof(float) + 255u) / 256u * 256u;
+    pf->bytes = pf->frame_bytes + 2u * rtiow::kMaxFoldDst * sizeof(unsigned int);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&pf->base), pf->bytes);  // plain cudaMalloc: exportable with CUDA IPC
+    if (e == cudaSuccess) e = cudaMemset(pf->base, 0, pf->bytes);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&pf->timed_out), sizeof(unsigned int), cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pf->done_ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        rtiow_b200_peer_frame_destroy(pf);
+        return set_err(RTIOW_ERR_CUDA, std::string("peer frame: ") + cudaGetErrorString(e));
+    }
+    *pf->timed_out = 0u;
+    pf->peer_base[rank] = pf->base;
+    pf->connected = n_ranks == 1;
+    *out = pf;
+    return RTIOW_OK;
+}
+
+int rtiow_b200_peer_frame_export(rtiow_peer_frame_t* pf, uint8_t* handle) {
+    if (!pf || !handle) return set_err(RTIOW_ERR_INVALID_ARG, "null argument");
+    CK(cudaSetDevice(pf->device));
+    PeerHandleWire w{};
+    CK(cudaIpcGetMemHandle(&w.ipc, pf->base));
+    w.pid = my_pid();
+    w.ptr = reinterpret_cast<uint64_t>(pf->base);
+    w.bytes = pf->bytes;
+    w.device = pf->device;
+    w.nx = pf->nx; w.ny = pf->ny; w.rank = pf->rank; w.n_ranks = pf->n_ranks;
+    w.magic = kPeerMagic;
+    std::memset(handle, 0, RTIOW_PEER_HANDLE_BYTES);
+    std::memcpy(handle, &w, sizeof(w));
+    return RTIOW_OK;
+}
+
+int rtiow_b200_peer_frame_connect(rtiow_peer_frame_t* pf, const uint8_t* handles) {
+    if (!pf || !handles) return set_err(RTIOW_ERR_INVALID_ARG, "null argument");
+    CK(cudaSetDevice(pf->device));
+    for (uint32_t q = 0; q < pf->n_ranks; ++q) {
+        PeerHandleWire w{};
+        std::memcpy(&w, handles + static_cast<size_t>(q) * RTIOW_PEER_HANDLE_BYTES, sizeof(w));
+        if (w.magic != kPeerMagic || w.rank != q || w.n_ranks != pf->n_ranks || w.nx != pf->nx || w.ny != pf->ny || w.bytes != pf->bytes)
+            return set_err(RTIOW_ERR_INVALID_ARG, "peer handle " + std::to_string(q) + " does not describe rank " + std::to_string(q) +
+                                                      " of this frame");
+        if (q == pf->rank) continue;
+        if (w.pid == my_pid()) {  // same process: the pointer itself, with peer access switched on
+            if (w.device != pf->device) {
+                int can = 0;
+                CK(cudaDeviceCanAccessPeer(&can, pf->device, w.device));
+                if (!can) return set_err(RTIOW_ERR_CUDA, "no peer access between devices " + std::to_string(pf->device) + " and " +
+                                                             std::to_string(w.device));
+                cudaError_t e = cudaDeviceEnablePeerAccess(w.device, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else if (e != cudaSuccess) return set_err(RTIOW_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+            }
+            pf->peer_base[q] = reinterpret_cast<unsigned char*>(w.ptr);
+        } else {
+            void* p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, w.ipc, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return set_err(RTIOW_ERR_CUDA, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(q) + "): " +
+                                                                     cudaGetErrorString(e));
+            pf->peer_base[q] = static_cast<unsigned char*>(p);
+            pf->opened_ipc[q] = true;
+        }
+    }
+    pf->connected = true;
+    return RTIOW_OK;
+}
+
+int rtiow_b200_peer_frame_ptr(rtiow_peer_frame_t* pf, float** d_frame) {
+    if (!pf || !d_frame) return set_err(RTIOW_ERR_INVALID_ARG, "null argument");
+    *d_frame = pf->frame(pf->rank);
+    return RTIOW_OK;
+}
+
+void rtiow_b200_peer_frame_destroy(rtiow_peer_frame_t* pf) {
+    if (!pf) return;
+    cudaSetDevice(pf->device);
+    cudaDeviceSynchronize();
+    for (uint32_t q = 0; q < pf->n_ranks; ++q)
+        if (pf->opened_ipc[q]) cudaIpcCloseMemHandle(pf->peer_base[q]);
+    if (pf->base) cudaFree(pf->base);
+    if (pf->timed_out) cudaFreeHost(pf->timed_out);
+    if (pf->done_ev) cudaEventDestroy(pf->done_ev);
+    delete pf;
+}
+
+}  // extern "C"
+namespace {
+void MultiFrames::destroy() {
+    for (rtiow_peer_frame_t* p : pf) rtiow_b200_peer_frame_destroy(p);
+    pf.clear();
+}
+}  // namespace
+extern "C" {
+
+int rtiow_b200_render_rows_peers(rtiow_scene_t* s, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny, uint32_t ns, uint64_t seed,
+                                 uint32_t band_rows, rtiow_peer_frame_t* pf, void* cuda_stream) {
+    if (!pf) return set_err(RTIOW_ERR_INVALID_ARG, "null argument");
+    if (int rc = check_render_args(s, cam, nx, ny, ns, 0, ny, pf, pf->n_ranks * std::max(1u, band_rows), std::max(1u, band_rows))) return rc;
+    if (band_rows == 0) return set_err(RTIOW_ERR_INVALID_ARG, "band_rows must be non-zero");
+    return render_bands(s, cam, nx, ny, ns, seed, band_rows, pf, (1u << pf->n_ranks) - 1u, true, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int rtiow_b200_render_multi(rtiow_scene_t* const* scenes, int ngpus, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny, uint32_t ns,
+                            uint64_t seed, float* out_rgb) {
+    if (!scenes || ngpus < 1 || ngpus > rtiow::kMaxFoldDst) return set_err(RTIOW_ERR_INVALID_ARG, "need 1 <= ngpus <= 16 scene handles");
+    for (int g = 0; g < ngpus; ++g)
+        if (!scenes[g]) return set_err(RTIOW_ERR_INVALID_ARG, "null scene handle");
+    if (int rc = check_render_args(scenes[0], cam, nx, ny, ns, 0, ny, out_rgb)) return rc;
+    if (ngpus == 1) return rtiow_b200_render(scenes[0], cam, nx, ny, ns, seed, out_rgb);
+    for (int g = 0; g < ngpus; ++g)
+        for (int h = 0; h < g; ++h)
+            if (scenes[g]->device == scenes[h]->device) return set_err(RTIOW_ERR_INVALID_ARG, "two scene handles on the same device");
+    // bands of 4 scanlines (the height of the kernel's work tiles) dealt round-robin: every GPU gets the same mix of cheap
+    // and expensive rows; single rows when the frame is too small for that to balance
+    const uint32_t G = static_cast<uint32_t>(ngpus);
+    const uint32_t band = ny >= 8u * rtiow::kTileH * G ? rtiow::kTileH : 1u;
+    // the devices' frames (GPU 0's is the one that gets assembled) are kept between calls of the same shape
+    std::vector<int> devices;
+    for (uint32_t g = 0; g < G; ++g) devices.push_back(scenes[g]->device);
+    std::lock_guard<std::mutex> lock(g_multi_mutex);
+    MultiFrames* mf = nullptr;
+    for (MultiFrames& c : g_multi_cache)
+        if (c.nx == nx && c.ny == ny && c.devices == devices) mf = &c;
+    int rc = RTIOW_OK;
+    if (!mf) {
+        while (g_multi_cache.size() >= 2) {
+            g_multi_cache.front().destroy();
+            g_multi_cache.erase(g_multi_cache.begin());
+        }
+        MultiFrames fresh;
+        fresh.nx = nx; fresh.ny = ny; fresh.devices = devices;
+        fresh.pf.assign(G, nullptr);
+        std::vector<uint8_t> handles(static_cast<size_t>(G) * RTIOW_PEER_HANDLE_BYTES);
+        for (uint32_t g = 0; g < G && rc == RTIOW_OK; ++g) {
+            rc = rtiow_b200_peer_frame_create(devices[g], nx, ny, g, G, &fresh.pf[g]);
+            if (rc == RTIOW_OK) rc = rtiow_b200_peer_frame_export(fresh.pf[g], handles.data() + static_cast<size_t>(g) * RTIOW_PEER_HANDLE_BYTES);
+        }
+        for (uint32_t g = 0; g < G && rc == RTIOW_OK; ++g) rc = rtiow_b200_peer_frame_connect(fresh.pf[g], handles.data());
+        if (rc != RTIOW_OK) {
+            const std::string keep = g_err;
+            fresh.destroy();
+            g_err = keep;
+            return rc;
+        }
+        g_multi_cache.push_back(fresh);
+        mf = &g_multi_cache.back();
+    }
+    std::vector<rtiow_peer_frame_t*>& pf = mf->pf;
+    // every GPU renders its bands and its fold stores them straight into GPU 0's frame (the only consumer here); one host
+    // thread drives all of them, the devices run concurrently
+    for (uint32_t g = 0; g < G && rc == RTIOW_OK; ++g) {
+        rc = render_bands(scenes[g], cam, nx, ny, ns, seed, band, pf[g], 1u, false, scenes[g]->ws->stream);
+        if (rc == RTIOW_OK && cudaEventRecord(pf[g]->done_ev, scenes[g]->ws->stream) != cudaSuccess) rc = set_err(RTIOW_ERR_CUDA, "cudaEventRecord");
+        if (rc == RTIOW_OK && scenes[g]->ws->mark_render_end(scenes[g]->ws->stream) != cudaSuccess) rc = set_err(RTIOW_ERR_CUDA, "cudaEventRecord");
+    }
+    if (rc == RTIOW_OK) {
+        Workspace& W0 = *scenes[0]->ws;
+        cudaError_t e = cudaSetDevice(scenes[0]->device);
+        for (uint32_t g = 1; g < G && e == cudaSuccess; ++g) e = cudaStreamWaitEvent(W0.stream, pf[g]->done_ev, 0);
+        if (e == cudaSuccess) e = W0.copy_to_host(out_rgb, pf[0]->frame(0), static_cast<size_t>(nx) * ny * 3 * sizeof(float));
+        if (e != cudaSuccess) rc = set_err(RTIOW_ERR_CUDA, std::string("render_multi gather: ") + cudaGetErrorString(e));
+    }
+    return rc;
 }
 
 int rtiow_b200_get_stats(rtiow_scene_t* s, rtiow_stats_t* out) {

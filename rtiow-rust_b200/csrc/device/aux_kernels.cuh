@@ -9,9 +9,22 @@ namespace rtiow {
 // Fold kernel: `(0..ns).map(..).sum()` then `col / ns as f32` (lib.rs:365-374, vec3.rs:195-203).
 // One thread per pixel walks its samples in order; staging is [sample][pixel] so a warp reads
 // 512 contiguous bytes per sample.
+//
+// Where the finished pixel goes: to `n` frames (this GPU's and, through NVLink peer pointers, the
+// other GPUs': the fold IS the framebuffer exchange, there is no all-gather behind it), either packed
+// (pixel p of the rendered row block -> p) or at the row's position in the whole image (packed row r
+// = image row row_begin + (r / row_band) * row_step + r % row_band).
 // ------------------------------------------------------------------------------------------------
+constexpr int kMaxFoldDst = 16;
+struct FoldDst {
+    float* p[kMaxFoldDst];
+    uint32_t n;
+    uint32_t image_rows;  // 0: packed; 1: rows land at their position in the ny x nx image
+    uint32_t nx, row_begin, row_step, row_band;
+};
+
 __global__ void __launch_bounds__(256) fold_kernel(const float4* __restrict__ staging, float4* __restrict__ accum,
-                                                   float* __restrict__ out_rgb, uint32_t npix, uint32_t s_count,
+                                                   const __grid_constant__ FoldDst dst, uint32_t npix, uint32_t s_count,
                                                    int first_pass, int last_pass, float ns_f,
                                                    unsigned long long* __restrict__ seg_total) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -26,9 +39,20 @@ __global__ void __launch_bounds__(256) fold_kernel(const float4* __restrict__ st
             segs += v.w;
         }
         if (last_pass) {
-            out_rgb[3u * p + 0u] = acc.x / ns_f;
-            out_rgb[3u * p + 1u] = acc.y / ns_f;
-            out_rgb[3u * p + 2u] = acc.z / ns_f;
+            size_t o = 3u * static_cast<size_t>(p);
+            if (dst.image_rows) {
+                const uint32_t r = p / dst.nx, x = p - r * dst.nx;
+                const uint32_t band = r / dst.row_band;
+                const uint32_t row = dst.row_begin + band * dst.row_step + (r - band * dst.row_band);
+                o = 3u * (static_cast<size_t>(row) * dst.nx + x);
+            }
+            const float cr = acc.x / ns_f, cg = acc.y / ns_f, cb = acc.z / ns_f;
+            for (uint32_t k = 0; k < dst.n; ++k) {
+                float* out = dst.p[k] + o;
+                out[0] = cr;
+                out[1] = cg;
+                out[2] = cb;
+            }
         } else {
             accum[p] = acc;
         }
@@ -37,6 +61,47 @@ __global__ void __launch_bounds__(256) fold_kernel(const float4* __restrict__ st
     unsigned long long w = static_cast<unsigned long long>(segs);
     for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
     if ((threadIdx.x & 31u) == 0u && w) atomicAdd(seg_total, w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cross-GPU hand-shake of the peer-store exchange (rtiow_b200_render_rows_peers).  Every rank owns
+// two flag arrays in its peer-visible allocation: flags[q] is written by rank q only.
+//   signal: after everything enqueued before it on the stream, publish `epoch` into MY slot of every
+//           rank's array (system-scope release);
+//   wait:   spin (system-scope acquire) until every slot of MY array has reached `epoch`, with a
+//           time-out so that a rank that never arrives cannot hang the GPU: *timed_out is set instead.
+// ------------------------------------------------------------------------------------------------
+struct PeerFlags {
+    unsigned int* p[kMaxFoldDst];  // rank q's flag array (peer pointer)
+    uint32_t n;
+};
+
+__global__ void peer_signal_kernel(const __grid_constant__ PeerFlags flags, uint32_t my_rank, unsigned int epoch) {
+    const uint32_t q = threadIdx.x;
+    __threadfence_system();  // the frame stores of the kernels before this one, cumulatively
+    if (q < flags.n) {
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags.p[q] + my_rank), "r"(epoch) : "memory");
+    }
+}
+
+__global__ void peer_wait_kernel(const unsigned int* __restrict__ my_flags, uint32_t n, unsigned int epoch,
+                                 unsigned long long timeout_ns, unsigned int* __restrict__ timed_out) {
+    const uint32_t q = threadIdx.x;
+    if (q >= n) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned int v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(my_flags + q) : "memory");
+        if (static_cast<int>(v - epoch) >= 0) break;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) {
+            atomicExch(timed_out, 1u);
+            break;
+        }
+        __nanosleep(200);
+    }
 }
 
 // Per-sample export for parity debugging: staging [s][pix] -> out [pix][ns_total][4]

@@ -13,7 +13,16 @@ Two partitions of the rows:
                          the all-gather is in place (BASELINE.json's "scanline block" wording); simpler, but
                          on the book-1 scene the top ranks finish early.
 
-No other collective exists on the path; with one rank nothing is exchanged at all.
+Two ways to exchange the rows:
+
+  peer stores (default)  the kernel that finishes a pixel (the in-order sample fold) stores it straight into EVERY
+                         rank's frame through NVLink peer pointers, at the row's final position
+                         (rtiow_b200_render_rows_peers): the exchange is fused into the fold, no collective is called
+                         on the data path, only the ranks' 128-byte frame handles are exchanged once at set-up.
+  NCCL                   one all_gather_into_tensor of the packed rows (+ one strided de-interleave copy for the
+                         interleaved partition): BASELINE.json's wording, kept as the cross-check and fallback.
+
+With one rank nothing is exchanged at all.
 """
 import ctypes as C
 
@@ -84,13 +93,86 @@ def assemble(parts, shard, xp=np):
     return torch.cat(pieces)
 
 
-class ShardBuffers:
-    """Device buffers of one rank, allocated once: `mine` (this rank's packed rows, padded to max_rows),
-    `parts` (everybody's), `frame` (the assembled image)."""
+class _DeviceArray:
+    """A raw device pointer as something torch.as_tensor understands."""
 
-    def __init__(self, nx, ny, shard, device, world=None):
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class PeerFrame:
+    """This rank's peer-visible frame (rtiow_b200_peer_frame_*): created on `device`, handles exchanged over the default
+    process group (any backend: 128 bytes per rank, once), peers mapped with CUDA IPC."""
+
+    def __init__(self, lib, nx, ny, device_index, rank, world_size, connect=True):
+        self.lib, self.nx, self.ny, self.device_index, self.world_size = lib, nx, ny, device_index, world_size
+        self.h = C.c_void_p()
+        api._check(lib.rtiow_b200_peer_frame_create(device_index, nx, ny, rank, world_size, C.byref(self.h)), lib)
+        mine = (C.c_uint8 * N.PEER_HANDLE_BYTES)()
+        api._check(lib.rtiow_b200_peer_frame_export(self.h, mine), lib)
+        self.handle = bytes(mine)
+        self.frame = None
+        if connect:
+            got = [self.handle]
+            if world_size > 1:
+                import torch.distributed as dist
+                got = [None] * world_size
+                dist.all_gather_object(got, self.handle)
+            self.connect(got)
+
+    def connect(self, handles):
+        """`handles`: every rank's `.handle`, in rank order."""
+        import torch
+        blob = (C.c_uint8 * (N.PEER_HANDLE_BYTES * self.world_size)).from_buffer_copy(b"".join(handles))
+        api._check(self.lib.rtiow_b200_peer_frame_connect(self.h, blob), self.lib)
+        ptr = C.c_void_p()
+        api._check(self.lib.rtiow_b200_peer_frame_ptr(self.h, C.byref(ptr)), self.lib)
+        self.frame = torch.as_tensor(_DeviceArray(ptr.value, (self.ny, self.nx, 3)), device=f"cuda:{self.device_index}")
+
+    def render(self, nx, ny, ns, camera, world, band_rows, seed=api.DEFAULT_SEED, stream=None):
+        """This rank's share (rtiow_b200_render_rows_peers), enqueued on `stream` (default: current)."""
+        import torch
+        s = stream if stream is not None else torch.cuda.current_stream(self.device_index)
+        api._check(self.lib.rtiow_b200_render_rows_peers(world.gpu(self.device_index), C.byref(camera.rec), nx, ny, ns, seed, band_rows,
+                                                         self.h, C.c_void_p(s.cuda_stream)), self.lib)
+
+    def close(self):
+        if self.h:
+            self.frame = None
+            self.lib.rtiow_b200_peer_frame_destroy(self.h)
+            self.h = None
+
+
+class ShardBuffers:
+    """Device buffers of one rank, allocated once.  Peer exchange: `frame` is this rank's peer-visible frame, every rank's
+    fold writes into it.  NCCL exchange: `mine` (this rank's packed rows, padded to max_rows), `parts` (everybody's),
+    `frame` (the assembled image)."""
+
+    def __init__(self, nx, ny, shard, device, world=None, exchange="auto"):
         import torch
         self.shard = shard
+        self.peer = None
+        dev_index = torch.device(device).index or 0
+        want_peer = exchange in ("auto", "peer") and shard.world_size > 1 and shard.interleaved and world is not None
+        if want_peer:
+            try:
+                self.peer = PeerFrame(world.lib, nx, ny, dev_index, shard.rank, shard.world_size)
+            except Exception as e:      # noqa: BLE001  no IPC / no peer access on this box: every rank must fall back together
+                if exchange == "peer":
+                    raise
+                self.peer, self.peer_error = None, str(e)
+            import torch.distributed as dist
+            ok = torch.tensor([1 if self.peer is not None else 0], device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok) == 0 and self.peer is not None:
+                self.peer.close()
+                self.peer = None
+        if self.peer is not None:
+            self.frame = self.peer.frame
+            self.mine = self.parts = None
+            self.exchange = ("fused into the sample fold: every finished row is stored into every rank's frame through NVLink peer "
+                             "pointers (rtiow_b200_render_rows_peers); no collective on the data path")
+            return
         self.frame = torch.empty((ny, nx, 3), dtype=torch.float32, device=device)
         self.exchange = "none (one rank)" if shard.world_size == 1 else "one NCCL all_gather_into_tensor of the packed rows" + (
             " + one strided de-interleave copy" if (shard.interleaved or not shard.uniform) else ", in place")
@@ -107,6 +189,9 @@ class ShardBuffers:
 
     def close(self):
         self.frame = self.mine = self.parts = None
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
 
 
 def render_sharded_device(nx, ny, ns, camera, world, bufs, seed=api.DEFAULT_SEED):
@@ -114,6 +199,9 @@ def render_sharded_device(nx, ny, ns, camera, world, bufs, seed=api.DEFAULT_SEED
     enqueued on the current stream; nothing is synchronised."""
     import torch.distributed as dist
     sh = bufs.shard
+    if bufs.peer is not None:
+        bufs.peer.render(nx, ny, ns, camera, world, sh.band, seed=seed)
+        return bufs.frame
     if sh.n_rows > 0:
         api.render_rows_device(nx, ny, ns, camera, world, bufs.mine, (sh.begin, sh.end), seed=seed, row_step=sh.step, row_band=sh.band)
     if sh.world_size > 1:
@@ -155,7 +243,7 @@ def par_cast_distributed(nx, ny, ns, camera, world, seed=api.DEFAULT_SEED, inter
     rank = dist.get_rank() if dist.is_initialized() else 0
     ws = dist.get_world_size() if dist.is_initialized() else 1
     dev = torch.cuda.current_device()
-    bufs = ShardBuffers(nx, ny, RowShard(ny, rank, ws, interleaved), f"cuda:{dev}")
+    bufs = ShardBuffers(nx, ny, RowShard(ny, rank, ws, interleaved), f"cuda:{dev}", world=world)
     render_sharded_device(nx, ny, ns, camera, world, bufs, seed=seed)
     return api.Image(bufs.frame.cpu().numpy())
 
