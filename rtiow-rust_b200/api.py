@@ -83,6 +83,7 @@ class World:
         self.name = name
         self.flavour = flavour      # which build of the device library renders it: "parity" (default) or "fast"
         self._gpu = {}
+        self._scene_bytes = {}
 
     @property
     def lib(self):
@@ -152,8 +153,11 @@ class World:
         _check(self.lib.rtiow_b200_set_traversal(self.gpu(device), int(mode)), self.lib)
 
     def scene_bytes(self, device=0):
-        """Bytes of the device image of the scene the last render used (uploaded by scene_create)."""
-        return self.stats(device)["scene_bytes"]
+        """Bytes of the device image of the scene the last render used (uploaded by scene_create).  Asked once per
+        device (rtiow_b200_get_stats synchronises the device); the image of a re-uploaded scene has the same size."""
+        if device not in self._scene_bytes:
+            self._scene_bytes[device] = self.stats(device)["scene_bytes"]
+        return self._scene_bytes[device]
 
     def stats(self, device=0):
         st = N.Stats()

@@ -389,7 +389,9 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     // Per-sample staging budget.  Automatic: up to 56 GiB, at most 70 % of what is free — a B200 has 180 GB and a
     // pass boundary costs a kernel tail, so C3 (10 GB), C4 (51 GB) and one rank's share of C5 (15 GB) are single passes.
     uint64_t budget = static_cast<uint64_t>(s->staging_mib) << 20;
-    if (s->staging_mib == 0) {
+    if (s->staging_mib == 0 && npix64 * ns * 16 <= W.staging.cap) {
+        budget = W.staging.cap;  // the whole frame fits what is already there: no need to ask the driver (cudaMemGetInfo is slow)
+    } else if (s->staging_mib == 0) {
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
         budget = std::min<uint64_t>(56ull << 30, (static_cast<uint64_t>(free_b) + W.staging.cap) / 10 * 7);

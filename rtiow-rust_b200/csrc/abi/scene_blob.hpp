@@ -15,6 +15,9 @@ namespace rtiow {
 //   a_w = 7 | (skip << 4)   skip = index of the item after the subtree's primitives
 //   a[0] = bits(root node index);  the subtree's primitive items follow, in stream order.
 constexpr uint32_t kItemAccel = 7u;
+// A leaf of a re-indexed subtree whose box is more than this many times the subtree's median leaf box becomes an
+// "ordered leaf" (see Compactor::run).
+constexpr float kFragileExtentRatio = 32.f;
 
 inline uint32_t bits_of(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 inline float float_of(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
@@ -162,6 +165,7 @@ struct BlobLayout {
     uint32_t off_nodes, off_frames, off_ops, off_mats, off_tex, off_pvecs, off_pperm;
     uint32_t off_fnodes;
     uint32_t n_items, n_nodes, n_accel, accel_depth;
+    uint32_t n_ordered; // leaves kept out of their re-indexed subtree, tested after it in the reference's order
     uint32_t n_prisms;  // rect_prism records, fused from six Rect items each or supplied as RTIOW_ITEM_PRISM
 };
 
@@ -251,7 +255,7 @@ struct Compactor {
     bool keep_leaf_boxes;  // kBlobFast: every leaf's own BBOX item stays in front of its primitives
     std::vector<rtiow_item_t> out;
     std::vector<AccelNode> nodes;
-    uint32_t n_accel = 0;
+    uint32_t n_accel = 0, n_ordered = 0;
     int max_depth = 0;
     bool odd_nesting = false;  // a skip link that leaves its enclosing box: the stream is shipped as it is
 
@@ -287,35 +291,76 @@ struct Compactor {
                 const uint32_t s = payload(i);
                 std::vector<RawLeaf> raw;
                 if (enable_accel && s <= end && d->n_items < (1u << 24) && classify(i, &raw)) {
+                    // Leaves whose box dwarfs the others' (book-1's radius-1000 ground sphere among radius-0.2 ones) stay OUT
+                    // of the tree: f32 cancellation makes such a primitive's t fall outside its own box's computed interval
+                    // often enough (1 sample in 4 M on book-1) that the result depends on whether the reference asked it
+                    // before or after a competing hit.  They follow the subtree as "ordered leaves" (BBOX item with
+                    // b_w = 1 + index of the first subtree item the reference visits after them), tested with exactly the
+                    // range the reference's order gives them (path_logic.cuh trav_stream).
+                    std::vector<char> fragile(raw.size(), 0);
+                    if (raw.size() >= 4) {
+                        std::vector<float> ext(raw.size());
+                        for (size_t k = 0; k < raw.size(); ++k) {
+                            const rtiow_item_t& bx = d->items[raw[k].box];
+                            ext[k] = std::fmax(std::fmax(bx.b[0] - bx.a[0], bx.b[1] - bx.a[1]), bx.b[2] - bx.a[2]);
+                        }
+                        std::vector<float> sorted = ext;
+                        std::nth_element(sorted.begin(), sorted.begin() + static_cast<std::ptrdiff_t>(sorted.size() / 2), sorted.end());
+                        const float median = sorted[sorted.size() / 2];
+                        size_t n_fragile = 0;
+                        for (size_t k = 0; k < raw.size(); ++k)
+                            if (!(ext[k] <= kFragileExtentRatio * median)) { fragile[k] = 1; ++n_fragile; }   // also NaN / inf
+                        if (raw.size() - n_fragile < 2) std::fill(fragile.begin(), fragile.end(), 0);
+                    }
                     const size_t at = out.size();
                     out.push_back(rtiow_item_t{});
                     std::vector<AccelLeaf> leaves;
                     leaves.reserve(raw.size());
-                    for (const RawLeaf& rl : raw) {  // stream order
+                    std::vector<uint32_t> next_regular(raw.size() + 1, 0);  // first tree item the reference visits after leaf k
+                    for (size_t k = 0; k < raw.size(); ++k) {  // stream order
+                        const RawLeaf& rl = raw[k];
+                        if (fragile[k]) continue;
                         AccelLeaf l{};
                         std::memcpy(l.mn, d->items[rl.box].a, 12);
                         std::memcpy(l.mx, d->items[rl.box].b, 12);
                         if (keep_leaf_boxes) {
                             rtiow_item_t box = d->items[rl.box];
                             box.a_w = RTIOW_ITEM_BBOX | (static_cast<uint32_t>(out.size() + 1 + (rl.end - rl.first)) << 4);
+                            box.b_w = 0;
                             out.push_back(box);
                         }
+                        next_regular[k] = static_cast<uint32_t>(out.size()) - (keep_leaf_boxes ? 1u : 0u);
                         l.first = static_cast<uint32_t>(out.size());
                         l.count = rl.end - rl.first;
                         for (uint32_t j = rl.first; j < rl.end; ++j) out.push_back(d->items[j]);
                         leaves.push_back(l);
                     }
+                    const uint32_t tree_end = static_cast<uint32_t>(out.size());
+                    next_regular[raw.size()] = tree_end;
+                    for (size_t k = raw.size(); k-- > 0;)
+                        if (fragile[k]) next_regular[k] = next_regular[k + 1];
                     int depth = 0;
                     const uint32_t root = accel_build(leaves, &nodes, &depth);
                     max_depth = depth > max_depth ? depth : max_depth;
                     rtiow_item_t& acc = out[at];
-                    acc.a_w = kItemAccel | (static_cast<uint32_t>(out.size()) << 4);
+                    acc.a_w = kItemAccel | (tree_end << 4);
                     std::memcpy(&acc.a[0], &root, 4);
                     ++n_accel;
+                    for (size_t k = 0; k < raw.size(); ++k) {  // the ordered leaves, in the reference's order
+                        if (!fragile[k]) continue;
+                        const RawLeaf& rl = raw[k];
+                        rtiow_item_t box = d->items[rl.box];
+                        box.a_w = RTIOW_ITEM_BBOX | (static_cast<uint32_t>(out.size() + 1 + (rl.end - rl.first)) << 4);
+                        box.b_w = next_regular[k] + 1u;
+                        out.push_back(box);
+                        for (uint32_t j = rl.first; j < rl.end; ++j) out.push_back(d->items[j]);
+                        ++n_ordered;
+                    }
                     i = s;
                 } else if (s <= end) {  // keep the box on the reference-order stream, recurse inside
                     const size_t at = out.size();
                     out.push_back(d->items[i]);
+                    out[at].b_w = 0;  // b_w of a BBOX item is the library's own (ordered-leaf marker)
                     run(i + 1, s);
                     out[at].a_w = RTIOW_ITEM_BBOX | (static_cast<uint32_t>(out.size()) << 4);
                     i = s;
@@ -371,6 +416,8 @@ inline std::vector<unsigned char> build_blob(const rtiow_scene_desc_t* d_in, boo
     if (cp.odd_nesting) {  // ship the stream as it is
         cp = blob_detail::Compactor{d, false, false, {}, {}};
         cp.out.assign(d->items, d->items + d->n_items);
+        for (rtiow_item_t& it : cp.out)
+            if ((it.a_w & 15u) == RTIOW_ITEM_BBOX) it.b_w = 0;
     }
     append(cp.out.data(), sizeof(rtiow_item_t) * cp.out.size());
     lay->n_items = static_cast<uint32_t>(cp.out.size());
@@ -388,6 +435,7 @@ inline std::vector<unsigned char> build_blob(const rtiow_scene_desc_t* d_in, boo
     }
     lay->n_nodes = static_cast<uint32_t>(cp.nodes.size());
     lay->n_accel = cp.n_accel;
+    lay->n_ordered = cp.n_ordered;
     lay->accel_depth = static_cast<uint32_t>(cp.max_depth);
     lay->off_frames = append(d->frames, sizeof(rtiow_frame_t) * d->n_frames);
     lay->off_ops = append(d->ops, sizeof(rtiow_xform_op_t) * d->n_ops);

@@ -497,6 +497,7 @@ struct Trav {
     int sp;            // stack height
     float best_t;      // t_range.end so far
     uint32_t best;     // winning item so far
+    uint32_t grp_end;  // end of the re-indexed subtree's own items (where its "ordered leaves" start), see trav_stream
     V3 fo, fd, inv;    // the ray in the current BBOX frame and its 1/d (aabb.rs:19)
     uint32_t f_id, f_nops;
     // conservative box test of the re-indexed subtrees (kFast traversal only; see trav_fast_setup)
@@ -521,6 +522,7 @@ RT_HD void trav_begin(V3 ro, V3 rd, Trav& tr) {
     tr.sp = 0;
     tr.best_t = kF32Max;
     tr.best = kNoHit;
+    tr.grp_end = 0u;
     tr.fo = ro;
     tr.fd = rd;
     tr.inv = mk(1.f / rd.x, 1.f / rd.y, 1.f / rd.z);
@@ -529,13 +531,14 @@ RT_HD void trav_begin(V3 ro, V3 rd, Trav& tr) {
     tr.fc = splat(0.f); tr.nbx = tr.nby = tr.nbz = 0u; tr.ek2 = 0.f; tr.omek = 0.f;
 }
 
-// Pop the next link worth visiting: entries the current best already beats are dropped (their box
-// test `end > start` would fail now, aabb.rs:27-28).
+// Pop the next link worth visiting: entries that start beyond the current best are dropped (their box test
+// `end > start` would fail now, aabb.rs:27-28).  An entry that starts exactly AT the best is still visited: it may
+// hold an item that ties with the best and comes earlier in the reference's order (such an item wins there).
 RT_HD void trav_pop(Trav& tr, const TravStack& stk) {
     tr.cur = kLinkNone;
     while (tr.sp > 0) {
         --tr.sp;
-        if (tr.best_t > stk.t[tr.sp]) {
+        if (tr.best_t >= stk.t[tr.sp]) {
             tr.cur = stk.link[tr.sp];
             break;
         }
@@ -555,9 +558,10 @@ RT_HD void trav_node_step(const SceneT<Mem, kFeat>& sc, Trav& tr, TravStack& stk
     const float4 q0 = sc.node_q(n, 0u), q1 = sc.node_q(n, 1u);
     const float4 q2 = sc.node_q(n, 2u), q3 = sc.node_q(n, 3u);
     float s0, s1;
-    const bool h0 = slab_test(q0, q1, tr.fo, tr.inv, tr.best_t, s0);
+    const float t_end = tr.best == kNoHit ? tr.best_t : next_up_pos(tr.best_t);  // a tie with the best may still win (earlier item)
+    const bool h0 = slab_test(q0, q1, tr.fo, tr.inv, t_end, s0);
     const uint32_t l0 = f2u(q0.w), l1 = f2u(q1.w);
-    const bool h1 = slab_test(q2, q3, tr.fo, tr.inv, tr.best_t, s1) && l1 != kLinkNone;
+    const bool h1 = slab_test(q2, q3, tr.fo, tr.inv, t_end, s1) && l1 != kLinkNone;
     if (h0 && h1) {
         const bool first0 = s0 <= s1;
         stk.link[tr.sp] = first0 ? l1 : l0;
@@ -683,7 +687,10 @@ RT_HD void trav_leaf_visit_fast(const SceneT<Mem, kFeat>& sc, const Path& path, 
     const uint32_t first = link & 0x00ffffffu;
     const float4 mn = sc.item_a(first - 1u), mx = sc.item_b(first - 1u);
     float start;
-    if (slab_test(mn, mx, tr.fo, trav_exact_inv<true>(tr), tr.best_t, start)) trav_leaf_test(sc, path, tr, link);
+    // t_range.end of the reference's leaf test is the nearest hit of the leaves BEFORE this one (bvh.rs:94-102): a best
+    // that comes later in the reference's order may tie with an item of this leaf, which then wins
+    const float t_end = (tr.best != kNoHit && first < (tr.best & kItemMask)) ? next_up_pos(tr.best_t) : tr.best_t;
+    if (slab_test(mn, mx, tr.fo, trav_exact_inv<true>(tr), t_end, start)) trav_leaf_test(sc, path, tr, link);
 }
 template <class Mem, uint32_t kFeat, class Path>
 RT_HD void trav_leaf_step_fast(const SceneT<Mem, kFeat>& sc, const Path& path, Trav& tr, const TravStack& stk) {  // requires trav_in_leaf(tr)
@@ -787,6 +794,13 @@ RT_HD_NOINLINE BestHit medium_hit(const SceneT<Mem, kFeat> sc, Rng rng, uint32_t
 // World::hit_top over the item stream, in the reference's visiting order (re-indexed subtrees are
 // order-free inside, see above).
 // ------------------------------------------------------------------------------------------------
+// Is the best hit so far an item that the reference visits AFTER the ordered leaf being tested (items [q, grp_end) of
+// the subtree it was taken out of)?
+RT_HD bool ordered_leaf_precedes_best(const Trav& tr, uint32_t q) {
+    const uint32_t b = tr.best & kItemMask;
+    return tr.best != kNoHit && b >= q && b < tr.grp_end;
+}
+
 // Interprets stream items from tr.i until a re-indexed subtree starts (tr.cur = its root) or the
 // stream ends (tr.i = kStreamEnd).
 template <bool kFrames, bool kFast, class Mem, uint32_t kFeat, class Path>
@@ -795,6 +809,7 @@ RT_HD void trav_stream(const SceneT<Mem, kFeat>& sc, const Path& path, Trav& tr)
     uint32_t pf_id = tr.f_id;
     V3 po = tr.fo, pd = tr.fd;
     uint32_t i = tr.i;
+    uint32_t ord_q = 0u, ord_end = 0u;  // inside an ordered leaf: items [ord_q, tr.grp_end) come after it in the reference's order
     for (;;) {
         const float4 ia = sc.item_a(i);
         const uint32_t kind = f2u(ia.w) & 15u;
@@ -802,6 +817,7 @@ RT_HD void trav_stream(const SceneT<Mem, kFeat>& sc, const Path& path, Trav& tr)
             tr.cur = f2u(ia.x);
             tr.sp = 0;
             i = f2u(ia.w) >> 4;
+            tr.grp_end = i;
             break;
         } else if (kind == IT_SPHERE || kind == IT_RECT || ((kFeat & SF_RECT) && kind == IT_PRISM)) {
             const float4 ib = sc.item_b(i);
@@ -820,7 +836,9 @@ RT_HD void trav_stream(const SceneT<Mem, kFeat>& sc, const Path& path, Trav& tr)
             }
             float t;
             uint32_t face = 0u;
-            if (prim_hit_t(sc, ia, ib, po, pd, path, frame, 0u, kNear, tr.best_t, t, face)) {
+            float t_hi = tr.best_t;
+            if ((kFeat & SF_ACCEL) && i < ord_end && ordered_leaf_precedes_best(tr, ord_q)) t_hi = next_up_pos(tr.best_t);
+            if (prim_hit_t(sc, ia, ib, po, pd, path, frame, 0u, kNear, t_hi, t, face)) {
                 tr.best_t = t;  // nearest = rec.t (lib.rs:42) / t_range.end = h.t (bvh.rs:98-100, object.rs:404-406)
                 tr.best = i | (face << 28);
             }
@@ -828,7 +846,19 @@ RT_HD void trav_stream(const SceneT<Mem, kFeat>& sc, const Path& path, Trav& tr)
         } else if (kind == IT_BBOX) {  // Aabb::hit  aabb.rs:18-29
             const float4 ib = sc.item_b(i);
             float start;
-            i = slab_test(ia, ib, tr.fo, trav_exact_inv<kFast>(tr), tr.best_t, start) ? i + 1u : (f2u(ia.w) >> 4);
+            float t_end = tr.best_t;
+            if ((kFeat & SF_ACCEL) && f2u(ib.w) != 0u) {
+                // An "ordered leaf" of the re-indexed subtree just walked (scene_blob.hpp): a leaf whose primitive is so
+                // large that its computed t can fall outside its own box's computed interval (the radius-1000 ground
+                // sphere of book-1), which makes the outcome depend on whether the reference tested it before or after a
+                // competing hit.  It is tested here, after the subtree, with the range the reference's order gives it:
+                // if the best so far comes LATER in that order, this leaf was asked first there — nothing could cull it,
+                // and its hit wins a tie.
+                ord_q = f2u(ib.w) - 1u;
+                ord_end = f2u(ia.w) >> 4;
+                if (ordered_leaf_precedes_best(tr, ord_q)) t_end = kF32Max;
+            }
+            i = slab_test(ia, ib, tr.fo, trav_exact_inv<kFast>(tr), t_end, start) ? i + 1u : (f2u(ia.w) >> 4);
         } else if ((kFeat & SF_MEDIUM) && kind == IT_MEDIUM) {
             const BestHit h = medium_hit(sc, path.rng(), path.bounce(), path.rtime(), i, tr.fo, tr.fd, tr.f_id, tr.f_nops, tr.best_t, tr.best);
             tr.best_t = h.t;

@@ -218,20 +218,30 @@ def par_cast_e2e(nx, ny, ns, camera, world, bufs, host_out, seed=api.DEFAULT_SEE
     H2D (fresh rtiow_b200_scene_create), rtiow_b200_render into `host_out` (numpy, pageable).  Several ranks:
     fresh scene upload, sharded render, all-gather, frame D2H into `host_out` (pinned torch tensor) on rank 0.
     Returns (h2d_bytes, d2h_bytes) of this rank."""
+    import os
+    import time
     import torch
     sh = bufs.shard
     dev = bufs.frame.device.index or 0
+    trace = os.environ.get("RTIOW_E2E_TRACE")
+    t0 = time.perf_counter()
     world.upload_fresh(dev)
+    t1 = time.perf_counter()
     if sh.world_size == 1:
         api._check(world.lib.rtiow_b200_render(world.gpu(dev), C.byref(camera.rec), nx, ny, ns, seed, host_out.ctypes.data), world.lib)
         return world.scene_bytes(dev) + C.sizeof(N.CameraRec), host_out.nbytes
     render_sharded_device(nx, ny, ns, camera, world, bufs, seed=seed)
-    h2d = world.scene_bytes(dev) + C.sizeof(N.CameraRec)
+    t2 = time.perf_counter()
     d2h = 0
     if sh.rank == 0:
         host_out.copy_(bufs.frame, non_blocking=True)
         d2h = bufs.frame.numel() * 4
     torch.cuda.current_stream(dev).synchronize()
+    t3 = time.perf_counter()
+    h2d = world.scene_bytes(dev) + C.sizeof(N.CameraRec)     # after the sync: get_stats synchronises the device
+    if trace:
+        print(f"e2e rank {sh.rank}: upload {1e3 * (t1 - t0):.3f} ms, enqueue {1e3 * (t2 - t1):.3f} ms, finish+d2h {1e3 * (t3 - t2):.3f} ms, "
+              f"stats {1e3 * (time.perf_counter() - t3):.3f} ms", flush=True)
     return h2d, d2h
 
 

@@ -27,7 +27,7 @@ static int harness_render_impl(const rtiow_scene_desc_t* desc, const rtiow_camer
     if (int rc = validate_desc(desc, &has_frames, &uses_perlin, &msg)) return rc;
     BlobLayout lay{};
     const std::vector<unsigned char> blob = build_blob(desc, uses_perlin, &lay, accel == 1 ? kBlobFast : (accel == 2 ? kBlobExact : kBlobReferenceOrder), g_fuse_prisms);
-    if (layout_out) { layout_out[0] = lay.n_items; layout_out[1] = lay.n_nodes; layout_out[2] = lay.n_accel; layout_out[3] = lay.accel_depth; layout_out[5] = lay.n_prisms; layout_out[6] = static_cast<uint32_t>(blob.size()); }
+    if (layout_out) { layout_out[0] = lay.n_items; layout_out[1] = lay.n_nodes; layout_out[2] = lay.n_accel; layout_out[3] = lay.accel_depth; layout_out[5] = lay.n_prisms; layout_out[6] = static_cast<uint32_t>(blob.size()); layout_out[7] = lay.n_ordered; }
     KParams P{};
     P.blob = blob.data();
     P.blob_bytes = static_cast<uint32_t>(blob.size());
@@ -146,4 +146,55 @@ extern "C" __attribute__((visibility("default"))) int harness_trace_rays(const r
         out[2 * i + 1] = best == kNoHit ? 0u : f2u(best_t);
     }
     return 0;
+}
+
+// Debug aid: one pixel-sample's path, segment by segment: out[8*k..] = {ox, oy, oz, dx, dy, dz, bits(t), winner item of THIS blob}.
+extern "C" __attribute__((visibility("default"))) int harness_trace_path(const rtiow_scene_desc_t* desc, const rtiow_camera_t* cam, uint32_t nx,
+                                                                         uint32_t ny, uint32_t x, uint32_t row, uint32_t sample, uint64_t seed,
+                                                                         int accel, float* out, uint32_t max_segments) {
+    using namespace rtiow;
+    g_fuse_prisms = (accel & 0x200) == 0;
+    accel &= 0xff;
+    bool has_frames = false, uses_perlin = false;
+    std::string msg;
+    if (int rc = validate_desc(desc, &has_frames, &uses_perlin, &msg)) return -rc;
+    BlobLayout lay{};
+    const std::vector<unsigned char> blob = build_blob(desc, uses_perlin, &lay, accel == 1 ? kBlobFast : (accel == 2 ? kBlobExact : kBlobReferenceOrder), g_fuse_prisms);
+    KParams P{};
+    P.blob = blob.data();
+    P.off_nodes = lay.off_nodes; P.off_frames = lay.off_frames; P.off_ops = lay.off_ops; P.off_mats = lay.off_mats; P.off_tex = lay.off_tex;
+    P.off_pvecs = lay.off_pvecs; P.off_pperm = lay.off_pperm; P.off_fnodes = lay.off_fnodes;
+    std::memcpy(P.cam, cam, sizeof(float) * 21);
+    P.nx = nx; P.ny = ny; P.row_begin = 0; P.row_step = 1; P.row_band = 1; P.n_rows = ny; P.npix = nx * ny;
+    P.key0 = static_cast<uint32_t>(seed); P.key1 = static_cast<uint32_t>(seed >> 32);
+    P.bg_kind = desc->background_kind;
+    std::memcpy(P.bg0, desc->background_c0, 12);
+    std::memcpy(P.bg1, desc->background_c1, 12);
+    const SceneT<MemPtr, SF_ALL> sc = scene_views<SF_ALL>(MemPtr{blob.data()}, P);
+    const bool fast = accel == 1;
+    PathState st;
+    st.pix = row * nx + x; st.samp = sample;
+    st.rng = Rng{P.key0, P.key1, 0u, 0u};
+    generate_camera_ray(P, st, x, row);
+    uint32_t n = 0;
+    for (; n < max_segments; ++n) {
+        float best_t = 0.f;
+        const V3 o = st.ro, d = st.rd;
+        const uint32_t best = has_frames ? (fast ? hit_top_stream<true, true>(sc, st, best_t) : hit_top_stream<true, false>(sc, st, best_t))
+                                         : (fast ? hit_top_stream<false, true>(sc, st, best_t) : hit_top_stream<false, false>(sc, st, best_t));
+        float* r = out + 8 * n;
+        r[0] = o.x; r[1] = o.y; r[2] = o.z; r[3] = d.x; r[4] = d.y; r[5] = d.z; r[6] = best == kNoHit ? 0.f : best_t;
+        uint32_t id = best;
+        if (best != kNoHit) {  // identify the winner by its record
+            const float4 a = sc.item_a(best & kItemMask), b = sc.item_b(best & kItemMask);
+            uint32_t h = 2166136261u;
+            const uint32_t w[6] = {f2u(a.x), f2u(b.x), f2u(b.y), f2u(b.z), f2u(b.w), best >> 28};
+            for (uint32_t k = 0; k < 6; ++k) h = (h ^ w[k]) * 16777619u;
+            id = h & 0x7fffffffu;
+        }
+        std::memcpy(&r[7], &id, 4);
+        V3 result;
+        if (shade_and_scatter(sc, P, st, best, best_t, result)) { ++n; break; }
+    }
+    return static_cast<int>(n);
 }

@@ -212,8 +212,8 @@ def test_reindexed_subtrees_layout():
         H.render(world, cam, 8, 8, 1, accel=accel, layout=lay)
         return world.counts(), dict(items=int(lay[0]), nodes=int(lay[1]), accels=int(lay[2]), depth=int(lay[3])), int(lay[5])
     c, l, _ = layout("book1", True)
-    assert l["accels"] == 1 and l["nodes"] == c["spheres"] - 1            # one leaf per sphere
-    assert l["items"] == c["spheres"] + 2 and l["depth"] <= 30            # ACCEL + spheres + END: no BBOX items left
+    assert l["accels"] == 1 and l["nodes"] == c["spheres"] - 2            # one leaf per sphere; the ground sphere stays outside
+    assert l["items"] == c["spheres"] + 3 and l["depth"] <= 30            # ACCEL + spheres + the ordered leaf's BBOX + END
     c, l, _ = layout("book1", True, accel=1)                              # fast tree: each leaf keeps its own BBOX item
     assert l["accels"] == 1 and l["items"] == 2 * c["spheres"] + 2
     c, l, prisms = layout("book1", True, accel=0)
@@ -277,6 +277,25 @@ def test_medium_boundary_validation():
     inner = media[2] + 1
     items[inner].a_w = 4 | (items[inner].a_w & ~15)                      # a medium inside a medium boundary
     assert lib.rtiow_b200_scene_validate(C.byref(d)) == N.ERR_INVALID_SCENE
+
+
+def test_ordered_leaves_keep_order_dependent_hits(oracle):
+    """book-1, pixel (x 192, row 89), sample 48 at 400x200: inside the glass sphere a ray reaches the point where that
+    sphere touches the radius-1000 ground sphere; f32 cancellation puts the ground hit (t = 0.7792329) BEFORE the entry of
+    the ground's own box (0.779288), with the glass sphere's exit (0.7792501) in between.  The reference asks the ground
+    first and keeps it; a nearer-first traversal that lets the later-found glass hit cull the ground's box loses it
+    (round 1 did: 1 sample in 4 M on book-1).  The ground sphere is therefore an "ordered leaf" (scene_blob.hpp) and
+    every traversal gives the oracle's bits."""
+    nx, ny, ns = 400, 200, 50
+    world, cam = R.build_scene("book1", nx, ny)
+    lay = np.zeros(8, np.uint32)
+    H.render(world, cam, 8, 8, 1, accel=1, layout=lay)
+    assert lay[7] == 1                                                   # exactly one ordered leaf: the ground
+    want, osmp, _ = oracle.Scene("book1", nx, ny).render(ns, nthreads=4, rows=(89, 90), want_samples=True)
+    for accel in (1, 2, 0):
+        got, smp = H.render(world, cam, nx, ny, ns, accel=accel, rows=(89, 90), want_samples=True)
+        assert n_diff(smp[..., :3], osmp) == 0 and n_diff(got, want) == 0, accel
+        assert smp[0, 192, 48, 3] == 17                                  # the path that used to run 25 segments
 
 
 def test_print_ppm_formatting(tmp_path, oracle):
