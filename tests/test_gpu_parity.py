@@ -374,15 +374,16 @@ def test_print_ppm_bytes_on_device(oracle):
 # and ~1e-3 of the final scene's (longer paths, media), and one diverged sample of 50 moves a pixel by more than one
 # 8-bit level — FMA contraction alone does exactly the same as FMA + approximate division.  So the gates are: the
 # SURVEY's mean bound where the scene's variance allows it, the PPM fraction as measured minus a margin, and for every
-# scene "much closer to the oracle's image than the Monte-Carlo noise of either".
+# scene "much closer to the oracle's image than the Monte-Carlo noise of either".  (kitchen_sink is left out on purpose: its
+# checker floor lies exactly in the plane y = 0, so the checker's sign(sin(10 y)) is the sign of a rounding error and an
+# FMA in `o + t * d` repaints whole squares — a property of that scene, not of the build.)
 # ---------------------------------------------------------------------------------------------------------------
 R2_MEAN_ABS_TOL = 1e-3
 
 
 @pytest.mark.parametrize("name,bvh,nx,ny,ns,ppm_within_1,mean_gate", [
     ("book1", True, 400, 200, 50, 0.985, True), ("cornell", False, 160, 160, 64, 0.995, True),
-    ("final", False, 160, 160, 64, 0.90, False), ("kitchen_sink", True, 160, 120, 64, 0.90, False),
-    ("cornell_smoke", False, 128, 128, 64, 0.90, False)])
+    ("final", False, 160, 160, 64, 0.90, False), ("cornell_smoke", False, 128, 128, 64, 0.90, False)])
 def test_fast_build_within_tolerance_of_the_oracle(oracle, name, bvh, nx, ny, ns, ppm_within_1, mean_gate):
     fast_world, cam = R.build_scene(name, nx, ny, use_bvh=bvh, flavour="fast")
     assert N.abi("fast").rtiow_b200_build_flavour().startswith(b"fast") and N.abi().rtiow_b200_build_flavour().startswith(b"parity")
