@@ -409,7 +409,12 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     const uint32_t smem_cap = static_cast<uint32_t>(s->max_smem_optin) - 1024u;
     rtiow::BlobMode mode = s->traversal == RTIOW_TRAVERSAL_REFERENCE_ORDER ? rtiow::kBlobReferenceOrder
                            : (s->traversal == RTIOW_TRAVERSAL_REINDEXED_EXACT ? rtiow::kBlobExact : rtiow::kBlobFast);
-    if (s->traversal == RTIOW_TRAVERSAL_REINDEXED && !s->force_global && blob_of(s, rtiow::kBlobFast).bytes > smem_cap &&
+    // The conservative-test tree is the larger image (112-byte nodes).  Shared memory and the L1 that caches the per-lane
+    // traversal stacks and register spills come out of the same 228 KB: a scene that fills it (final scene: 208 KB) runs
+    // 30 % SLOWER with the cheaper box test than with the exact-test tree (140 KB) — measured, profiles/r02 — so the
+    // conservative tree is used only while it leaves a third of the array to the L1.
+    const uint32_t fast_cap = smem_cap / 3u * 2u;
+    if (s->traversal == RTIOW_TRAVERSAL_REINDEXED && !s->force_global && blob_of(s, rtiow::kBlobFast).bytes > fast_cap &&
         blob_of(s, rtiow::kBlobExact).bytes <= smem_cap)
         mode = rtiow::kBlobExact;
     rtiow_scene::Blob& B = blob_of(s, mode);
@@ -419,15 +424,22 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     // 0 = automatic: one CTA per SM; 768 threads (80 registers) for the general kernel, 1024 (64 registers) for the
     // spheres-only one, which needs no more
     // kernel profile: the smallest compiled feature mask that covers the scene (the re-indexed subtrees add SF_ACCEL)
-    const uint32_t needs = s->features | (B.lay.n_accel ? static_cast<uint32_t>(rtiow::SF_ACCEL) : 0u);
+    const uint32_t needs = s->features | (B.lay.n_accel ? static_cast<uint32_t>(rtiow::SF_ACCEL) : 0u) |
+                           (B.lay.n_ordered ? static_cast<uint32_t>(rtiow::SF_ORDERED) : 0u);
     uint32_t profile = 0;
-    if (s->specialise && !s->has_frames) {
-        if ((needs & ~rtiow::kFeatSpheres) == 0u) profile = 1;
-        else if ((needs & ~rtiow::kFeatRects) == 0u) profile = 2;
+    if (s->specialise) {
+        if (!s->has_frames && (needs & ~rtiow::kFeatSpheres) == 0u) profile = 1;
+        else if (!s->has_frames && (needs & ~rtiow::kFeatRects) == 0u) profile = 2;
+        else if (smem && (needs & ~rtiow::kFeatLean) == 0u) profile = 3;  // the general kernel minus what this scene cannot contain
     }
-    const uint32_t threads = s->cta_threads ? s->cta_threads : (profile ? 1024u : 768u);
-    const KernelVariant var = smem ? rtiow::pick_plain_smem(s->has_frames, fast, profile, threads)
-                                   : rtiow::pick_plain_global(s->has_frames, fast, profile, threads);
+    const uint32_t threads = s->cta_threads ? s->cta_threads : ((profile == 1u || profile == 2u) ? 1024u : 768u);
+    KernelVariant var = profile == 3u ? rtiow::pick_lean_smem(s->has_frames, fast, threads)
+                                      : (smem ? rtiow::pick_plain_smem(s->has_frames, fast, profile, threads)
+                                              : rtiow::pick_plain_global(s->has_frames, fast, profile, threads));
+    if (!var.fn && profile == 3u) {  // no lean instantiation for this CTA size: the general kernel renders the same image
+        profile = 0;
+        var = rtiow::pick_plain_smem(s->has_frames, fast, profile, threads);
+    }
     if (!var.fn) return set_err(RTIOW_ERR_INVALID_ARG, "no kernel instantiation for this cta_threads");
     const size_t dyn_smem = smem ? B.bytes : 0;
     int num_regs = 0;

@@ -139,7 +139,7 @@ inline int validate_desc(const rtiow_scene_desc_t* d, bool* has_frames, bool* us
 // How Bvh subtrees are laid out for the device (rtiow_b200.h RTIOW_TRAVERSAL_*).
 enum BlobMode { kBlobFast = 0, kBlobReferenceOrder = 1, kBlobExact = 2 };
 
-// The features of a scene (path_logic.cuh SF_*), without SF_ACCEL (that depends on how the blob is built).
+// The features of a scene (path_logic.cuh SF_*), without SF_ACCEL and SF_ORDERED (they depend on how the blob is built).
 inline uint32_t scene_features(const rtiow_scene_desc_t* d) {
     uint32_t f = 0;
     auto wrapped = [&](uint32_t frame) { return frame < d->n_frames && d->frames[frame].n_ops != 0; };
@@ -147,7 +147,11 @@ inline uint32_t scene_features(const rtiow_scene_desc_t* d) {
         const uint32_t kind = d->items[i].a_w & 15u, payload = d->items[i].a_w >> 4;
         if (kind == RTIOW_ITEM_SPHERE) f |= 1u | (wrapped(payload) ? 4u : 0u);
         else if (kind == RTIOW_ITEM_RECT || kind == RTIOW_ITEM_PRISM) f |= 2u | (wrapped(payload) ? 4u : 0u);
-        else if (kind == RTIOW_ITEM_MEDIUM) f |= 8u | (wrapped(payload) ? 4u : 0u);
+        else if (kind == RTIOW_ITEM_MEDIUM) {
+            f |= 8u | (wrapped(payload) ? 4u : 0u);
+            const uint32_t run_end = bits_of(d->items[i].a[2]);
+            if (run_end != i + 2u || (i + 1u < d->n_items && (d->items[i + 1u].a_w & 15u) == RTIOW_ITEM_BBOX)) f |= 512u;  // SF_MEDIUM_RUN
+        }
         else if (kind == RTIOW_ITEM_SET_FRAME) f |= 4u;
     }
     for (uint32_t m = 0; m < d->n_materials; ++m) {
@@ -158,6 +162,10 @@ inline uint32_t scene_features(const rtiow_scene_desc_t* d) {
         if (mt.kind == RTIOW_MAT_ISOTROPIC) f |= 64u;
         if (mt.kind == RTIOW_MAT_METAL || mt.kind == RTIOW_MAT_DIELECTRIC) f |= 128u;
     }
+    for (uint32_t t = 0; t < d->n_textures; ++t)
+        if (d->textures[t].kind == RTIOW_TEX_CHECKER) f |= 2048u;  // SF_CHECKER
+    for (uint32_t k = 0; k < d->n_ops; ++k)
+        if (d->ops[k].kind == RTIOW_OP_SCALE) f |= 4096u;          // SF_SCALE
     return f;
 }
 
@@ -165,6 +173,7 @@ struct BlobLayout {
     uint32_t off_nodes, off_frames, off_ops, off_mats, off_tex, off_pvecs, off_pperm;
     uint32_t off_fnodes;
     uint32_t n_items, n_nodes, n_accel, accel_depth;
+    uint32_t n_derived; // leaves whose box is derived from their primitive's record (no BBOX item)
     uint32_t n_ordered; // leaves kept out of their re-indexed subtree, tested after it in the reference's order
     uint32_t n_prisms;  // rect_prism records, fused from six Rect items each or supplied as RTIOW_ITEM_PRISM
 };
@@ -187,6 +196,37 @@ namespace blob_detail {
 // shared-memory footprint (the final scene's 400 boxes: 77 KB -> 13 KB).
 // ---------------------------------------------------------------------------------------------
 inline bool same_bits(float a, float b) { return bits_of(a) == bits_of(b); }
+
+// Internal primitive flag (never part of the ABI): the primitive is alone in a leaf of a re-indexed subtree and the
+// leaf's box — the reference's `bounding_box()` of that object — is what the record itself yields:
+//   Translate{Sphere}: (-r + offset, r + offset)      object.rs:113-118, 285-291
+//   rect_prism:        (p0 - 0.0001, p1 + 0.0001)     object.rs:220-233 merged by And (object.rs:412-416)
+// checked bit for bit against the BBOX item the host sent, which is then dropped: a leaf visit loads one record instead
+// of two (path_logic.cuh trav_leaf_visit_fast) and the scene needs 32 bytes less shared memory per leaf.
+constexpr uint32_t kFlagBoxDerived = 16u;
+
+inline bool leaf_box_is_derivable(const rtiow_item_t& box, const rtiow_item_t& prim) {
+    const uint32_t kind = prim.a_w & 15u, flags = prim.b_w >> 24;
+    float mn[3], mx[3];
+    if (kind == RTIOW_ITEM_SPHERE) {
+        const float r = prim.a[0];
+        for (int a = 0; a < 3; ++a) {
+            const float off = (flags & RTIOW_FLAG_HAS_OFFSET) ? prim.b[a] : 0.f;
+            mn[a] = (flags & RTIOW_FLAG_HAS_OFFSET) ? -r + off : -r;
+            mx[a] = (flags & RTIOW_FLAG_HAS_OFFSET) ? r + off : r;
+        }
+    } else if (kind == RTIOW_ITEM_PRISM) {
+        for (int a = 0; a < 3; ++a) {
+            mn[a] = prim.a[a] - 0.0001f;
+            mx[a] = prim.b[a] + 0.0001f;
+        }
+    } else {
+        return false;
+    }
+    for (int a = 0; a < 3; ++a)
+        if (!same_bits(mn[a], box.a[a]) || !same_bits(mx[a], box.b[a])) return false;
+    return true;
+}
 
 inline bool is_prism_run(const rtiow_item_t* it, rtiow_item_t* fused) {
     static const uint32_t axes[6] = {2u, 1u, 0u, 2u, 1u, 0u};
@@ -255,8 +295,10 @@ struct Compactor {
     bool keep_leaf_boxes;  // kBlobFast: every leaf's own BBOX item stays in front of its primitives
     std::vector<rtiow_item_t> out;
     std::vector<AccelNode> nodes;
-    uint32_t n_accel = 0, n_ordered = 0;
+    uint32_t n_accel = 0, n_ordered = 0, n_derived = 0;
     int max_depth = 0;
+    bool derive_leaf_boxes = true;
+    uint32_t frame_of_box = 0;  // the frame the BBOX items of the subtree being compacted live in
     bool odd_nesting = false;  // a skip link that leaves its enclosing box: the stream is shipped as it is
 
     uint32_t kind(uint32_t i) const { return d->items[i].a_w & 15u; }
@@ -323,16 +365,23 @@ struct Compactor {
                         AccelLeaf l{};
                         std::memcpy(l.mn, d->items[rl.box].a, 12);
                         std::memcpy(l.mx, d->items[rl.box].b, 12);
-                        if (keep_leaf_boxes) {
+                        // the frame of the prim must be the subtree's (no wrapper between the Bvh and the leaf object)
+                        const bool derived = keep_leaf_boxes && derive_leaf_boxes && rl.end - rl.first == 1 &&
+                                             (d->items[rl.first].a_w >> 4) == frame_of_box && leaf_box_is_derivable(d->items[rl.box], d->items[rl.first]);
+                        if (keep_leaf_boxes && !derived) {
                             rtiow_item_t box = d->items[rl.box];
                             box.a_w = RTIOW_ITEM_BBOX | (static_cast<uint32_t>(out.size() + 1 + (rl.end - rl.first)) << 4);
                             box.b_w = 0;
                             out.push_back(box);
                         }
-                        next_regular[k] = static_cast<uint32_t>(out.size()) - (keep_leaf_boxes ? 1u : 0u);
+                        next_regular[k] = static_cast<uint32_t>(out.size()) - ((keep_leaf_boxes && !derived) ? 1u : 0u);
                         l.first = static_cast<uint32_t>(out.size());
                         l.count = rl.end - rl.first;
                         for (uint32_t j = rl.first; j < rl.end; ++j) out.push_back(d->items[j]);
+                        if (derived) {
+                            out.back().b_w |= kFlagBoxDerived << 24;
+                            ++n_derived;
+                        }
                         leaves.push_back(l);
                     }
                     const uint32_t tree_end = static_cast<uint32_t>(out.size());
@@ -380,6 +429,7 @@ struct Compactor {
                 out[at].a[2] = float_of(static_cast<uint32_t>(out.size()));
                 i = run_end;
             } else {
+                if (k == RTIOW_ITEM_SET_FRAME) frame_of_box = payload(i);
                 out.push_back(d->items[i]);
                 i += 1;
             }
@@ -436,6 +486,7 @@ inline std::vector<unsigned char> build_blob(const rtiow_scene_desc_t* d_in, boo
     lay->n_nodes = static_cast<uint32_t>(cp.nodes.size());
     lay->n_accel = cp.n_accel;
     lay->n_ordered = cp.n_ordered;
+    lay->n_derived = cp.n_derived;
     lay->accel_depth = static_cast<uint32_t>(cp.max_depth);
     lay->off_frames = append(d->frames, sizeof(rtiow_frame_t) * d->n_frames);
     lay->off_ops = append(d->ops, sizeof(rtiow_xform_op_t) * d->n_ops);

@@ -27,7 +27,7 @@ enum : uint32_t { IT_END = 0, IT_BBOX = 1, IT_SPHERE = 2, IT_RECT = 3, IT_MEDIUM
 constexpr uint32_t kItemMask = 0x0fffffffu;
 constexpr uint32_t kLinkLeafBit = 0x80000000u, kLinkNone = 0x7fffffffu;  // accel_build.hpp
 constexpr int kStackDepth = 32;
-enum : uint32_t { FL_HAS_OFFSET = 1u, FL_FLIP = 2u };
+enum : uint32_t { FL_HAS_OFFSET = 1u, FL_FLIP = 2u, FL_BOX_DERIVED = 16u };  // bits 2..3: rect axis; 16: scene_blob.hpp kFlagBoxDerived
 enum : uint32_t { OP_TRANSLATE = 0, OP_SCALE = 1, OP_ROTATE_Y = 2, OP_LINEAR_MOVE = 3, OP_FLIP = 4 };
 enum : uint32_t { MAT_LAMBERTIAN = 0, MAT_METAL = 1, MAT_DIELECTRIC = 2, MAT_DIFFUSE_LIGHT = 3, MAT_ISOTROPIC = 4 };
 enum : uint32_t { TEX_CONSTANT = 0, TEX_CHECKER = 1, TEX_PERLIN = 2 };
@@ -108,10 +108,18 @@ enum : uint32_t {
     SF_ISOTROPIC = 64u,  // Isotropic
     SF_SPECULAR = 128u,  // Metal, Dielectric
     SF_ACCEL = 256u,     // re-indexed Bvh subtrees (node / leaf traversal with a per-lane stack)
-    SF_ALL = 511u
+    SF_MEDIUM_RUN = 512u,  // a ConstantMedium whose boundary is more than one primitive (a rect_prism, a Bvh)
+    SF_ORDERED = 1024u,  // ordered leaves behind a re-indexed subtree (scene_blob.hpp)
+    SF_CHECKER = 2048u,  // checker texture (f32::sin in double precision)
+    SF_SCALE = 4096u,    // Scale wrapper (six IEEE divisions each way)
+    SF_ALL = 8191u
 };
-constexpr uint32_t kFeatSpheres = SF_SPHERE | SF_SPECULAR | SF_ACCEL;  // book-1
-constexpr uint32_t kFeatRects = SF_RECT | SF_WRAP | SF_LIGHT;          // Cornell box
+constexpr uint32_t kFeatSpheres = SF_SPHERE | SF_SPECULAR | SF_ACCEL | SF_ORDERED;  // book-1
+constexpr uint32_t kFeatRects = SF_RECT | SF_WRAP | SF_LIGHT;                       // Cornell box
+// Everything except what the reference's own scenes never build.  The general kernel is bound by instruction fetch
+// (4-5 k SASS instructions against a 32 KB instruction cache): every rare feature that is compiled in costs the final
+// scene several percent although it never executes (measured: profiles/r02, bisect of the round-2 additions).
+constexpr uint32_t kFeatLean = SF_ALL & ~(SF_MEDIUM_RUN | SF_ORDERED | SF_CHECKER | SF_SCALE);
 
 // Views into the scene blob.
 template <class Mem, uint32_t kFeat = SF_ALL>
@@ -167,12 +175,13 @@ struct PathStateView {
     RT_HD uint32_t bounce() const { return st->bounce; }
 };
 
+template <bool kScale>
 RT_HD void apply_op_ray(const float4 op, V3& o, V3& d, float time) {
     const uint32_t kind = f2u(op.x);
     const V3 v = mk(op.y, op.z, op.w);
     if (kind == OP_TRANSLATE) {            // object.rs:275-278
         o = o - v;
-    } else if (kind == OP_SCALE) {         // object.rs:309-313
+    } else if (kScale && kind == OP_SCALE) {         // object.rs:309-313
         o = o / v;
         d = d / v;
     } else if (kind == OP_ROTATE_Y) {      // object.rs:357-361
@@ -183,12 +192,13 @@ RT_HD void apply_op_ray(const float4 op, V3& o, V3& d, float time) {
     }
 }
 
+template <bool kScale>
 RT_HD void apply_op_hit(const float4 op, V3& p, V3& n) {
     const uint32_t kind = f2u(op.x);
     const V3 v = mk(op.y, op.z, op.w);
     if (kind == OP_TRANSLATE) {            // object.rs:279-282
         p = p + v;
-    } else if (kind == OP_SCALE) {         // object.rs:314-318
+    } else if (kScale && kind == OP_SCALE) {         // object.rs:314-318
         p = p * v;
         n = n / v;
     } else if (kind == OP_ROTATE_Y) {      // object.rs:365-369
@@ -205,14 +215,14 @@ RT_HD void apply_op_hit(const float4 op, V3& p, V3& n) {
 struct Ray6 {
     V3 o, d;
 };
-template <class Mem>
+template <uint32_t kFeat, class Mem>
 RT_HD_NOINLINE Ray6 frame_ops_ray(Mem m, uint32_t first_off, uint32_t n, V3 o, V3 d, float time) {
-    for (uint32_t k = 0; k < n; ++k) apply_op_ray(m.ld4(first_off + 16u * k), o, d, time);  // outermost first
+    for (uint32_t k = 0; k < n; ++k) apply_op_ray<(kFeat & SF_SCALE) != 0u>(m.ld4(first_off + 16u * k), o, d, time);  // outermost first
     return Ray6{o, d};
 }
-template <class Mem>
+template <uint32_t kFeat, class Mem>
 RT_HD_NOINLINE Ray6 frame_ops_hit(Mem m, uint32_t first_off, uint32_t n, V3 p, V3 nrm) {
-    for (uint32_t k = n; k > 0u; --k) apply_op_hit(m.ld4(first_off + 16u * (k - 1u)), p, nrm);  // innermost first
+    for (uint32_t k = n; k > 0u; --k) apply_op_hit<(kFeat & SF_SCALE) != 0u>(m.ld4(first_off + 16u * (k - 1u)), p, nrm);  // innermost first
     return Ray6{p, nrm};
 }
 
@@ -313,7 +323,7 @@ RT_HD bool prim_hit_t(const SceneT<Mem, kFeat>& sc, float4 ia, float4 ib, V3 o, 
     if (kFeat & SF_WRAP) {
         if (frame != cur_frame) {
             const uint2 fr = sc.frame(frame);
-            const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * (fr.x + cur_nops), fr.y - cur_nops, o, d, path.rtime());
+            const Ray6 r = frame_ops_ray<kFeat>(sc.m, sc.off_ops + 16u * (fr.x + cur_nops), fr.y - cur_nops, o, d, path.rtime());
             o = r.o;
             d = r.d;
         }
@@ -376,7 +386,7 @@ RT_HD_NOINLINE V3 texture_eval(const SceneT<Mem, kFeat>& sc, uint32_t id, V3 p) 
         const uint32_t kind = f2u(t0.x);
         if (kind == TEX_CONSTANT) return mk(t0.y, t0.z, t0.w);            // texture.rs:8-10
         const float4 t1 = sc.tex(id, 1u);
-        if (kind == TEX_PERLIN) return splat(perlin_turb(sc, t1.x * p));  // texture.rs:23-26
+        if (!(kFeat & SF_CHECKER) || kind == TEX_PERLIN) return splat(perlin_turb(sc, t1.x * p));  // texture.rs:23-26
         const V3 q = 10.f * p;                                            // checker, texture.rs:12-21
         const float s = (sin_f32(q.x) * sin_f32(q.y)) * sin_f32(q.z);
         id = s < 0.f ? f2u(t1.z) : f2u(t1.y);
@@ -685,7 +695,25 @@ RT_HD void trav_node_step_fast(const SceneT<Mem, kFeat>& sc, Trav& tr, TravStack
 template <class Mem, uint32_t kFeat, class Path>
 RT_HD void trav_leaf_visit_fast(const SceneT<Mem, kFeat>& sc, const Path& path, Trav& tr, uint32_t link) {
     const uint32_t first = link & 0x00ffffffu;
-    const float4 mn = sc.item_a(first - 1u), mx = sc.item_b(first - 1u);
+    // The leaf's own box: the BBOX item in front of its primitives, or — a lone Translate{Sphere} / rect_prism, checked at
+    // scene upload (scene_blob.hpp leaf_box_is_derivable) — the reference's bounding_box() recomputed from the record.
+    const float4 pa = sc.item_a(first), pb = sc.item_b(first);
+    const uint32_t pflags = f2u(pb.w) >> 24;
+    float4 mn, mx;
+    if (pflags & FL_BOX_DERIVED) {
+        if ((kFeat & SF_SPHERE) && (!(kFeat & SF_RECT) || (f2u(pa.w) & 15u) == IT_SPHERE)) {
+            const bool has = (pflags & FL_HAS_OFFSET) != 0u;  // object.rs:113-118, 285-291
+            const float r = pa.x, ox = has ? pb.x : 0.f, oy = has ? pb.y : 0.f, oz = has ? pb.z : 0.f;
+            mn = make_float4(has ? -r + ox : -r, has ? -r + oy : -r, has ? -r + oz : -r, 0.f);
+            mx = make_float4(has ? r + ox : r, has ? r + oy : r, has ? r + oz : r, 0.f);
+        } else {                                              // object.rs:220-233 merged by And (412-416)
+            mn = make_float4(pa.x - 0.0001f, pa.y - 0.0001f, pa.z - 0.0001f, 0.f);
+            mx = make_float4(pb.x + 0.0001f, pb.y + 0.0001f, pb.z + 0.0001f, 0.f);
+        }
+    } else {
+        mn = sc.item_a(first - 1u);
+        mx = sc.item_b(first - 1u);
+    }
     float start;
     // t_range.end of the reference's leaf test is the nearest hit of the leaves BEFORE this one (bvh.rs:94-102): a best
     // that comes later in the reference's order may tie with an item of this leaf, which then wins
@@ -757,7 +785,7 @@ RT_HD_NOINLINE BestHit medium_hit(const SceneT<Mem, kFeat> sc, Rng rng, uint32_t
     uint32_t m_nops = f_nops;
     if (mframe != f_id) {
         const uint2 fr = sc.frame(mframe);
-        const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * (fr.x + f_nops), fr.y - f_nops, mo, md, time);
+        const Ray6 r = frame_ops_ray<kFeat>(sc.m, sc.off_ops + 16u * (fr.x + f_nops), fr.y - f_nops, mo, md, time);
         mo = r.o;
         md = r.d;
         m_nops = fr.y;
@@ -766,7 +794,7 @@ RT_HD_NOINLINE BestHit medium_hit(const SceneT<Mem, kFeat> sc, Rng rng, uint32_t
     float t1, t2;
     bool both;
     const float4 ba = sc.item_a(i + 1u), bb = sc.item_b(i + 1u);
-    if (run_end == i + 2u && (f2u(ba.w) & 15u) != IT_BBOX) {  // the usual boundary, one primitive (a sphere of fog): no run to walk
+    if (!(kFeat & SF_MEDIUM_RUN) || (run_end == i + 2u && (f2u(ba.w) & 15u) != IT_BBOX)) {  // the usual boundary, one primitive (a sphere of fog): no run to walk
         both = prim_hit_outline(sc, ba, bb, mo, md, time, mframe, m_nops, kF32Min, kF32Max, t1) &&
                prim_hit_outline(sc, ba, bb, mo, md, time, mframe, m_nops, t1 + 0.0001f, kF32Max, t2);
     } else {
@@ -828,7 +856,7 @@ RT_HD void trav_stream(const SceneT<Mem, kFeat>& sc, const Path& path, Trav& tr)
                     pd = tr.fd;
                 } else {
                     const uint2 fr = sc.frame(frame);
-                    const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * (fr.x + tr.f_nops), fr.y - tr.f_nops, tr.fo, tr.fd, path.rtime());
+                    const Ray6 r = frame_ops_ray<kFeat>(sc.m, sc.off_ops + 16u * (fr.x + tr.f_nops), fr.y - tr.f_nops, tr.fo, tr.fd, path.rtime());
                     po = r.o;
                     pd = r.d;
                 }
@@ -837,7 +865,7 @@ RT_HD void trav_stream(const SceneT<Mem, kFeat>& sc, const Path& path, Trav& tr)
             float t;
             uint32_t face = 0u;
             float t_hi = tr.best_t;
-            if ((kFeat & SF_ACCEL) && i < ord_end && ordered_leaf_precedes_best(tr, ord_q)) t_hi = next_up_pos(tr.best_t);
+            if ((kFeat & SF_ORDERED) && i < ord_end && ordered_leaf_precedes_best(tr, ord_q)) t_hi = next_up_pos(tr.best_t);
             if (prim_hit_t(sc, ia, ib, po, pd, path, frame, 0u, kNear, t_hi, t, face)) {
                 tr.best_t = t;  // nearest = rec.t (lib.rs:42) / t_range.end = h.t (bvh.rs:98-100, object.rs:404-406)
                 tr.best = i | (face << 28);
@@ -847,7 +875,7 @@ RT_HD void trav_stream(const SceneT<Mem, kFeat>& sc, const Path& path, Trav& tr)
             const float4 ib = sc.item_b(i);
             float start;
             float t_end = tr.best_t;
-            if ((kFeat & SF_ACCEL) && f2u(ib.w) != 0u) {
+            if ((kFeat & SF_ORDERED) && f2u(ib.w) != 0u) {
                 // An "ordered leaf" of the re-indexed subtree just walked (scene_blob.hpp): a leaf whose primitive is so
                 // large that its computed t can fall outside its own box's computed interval (the radius-1000 ground
                 // sphere of book-1), which makes the outcome depend on whether the reference tested it before or after a
@@ -868,7 +896,7 @@ RT_HD void trav_stream(const SceneT<Mem, kFeat>& sc, const Path& path, Trav& tr)
             if (kFrames) {
                 tr.f_id = f2u(ia.w) >> 4;
                 const uint2 fr = sc.frame(tr.f_id);
-                const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * fr.x, fr.y, path.ro(), path.rd(), path.rtime());
+                const Ray6 r = frame_ops_ray<kFeat>(sc.m, sc.off_ops + 16u * fr.x, fr.y, path.ro(), path.rd(), path.rtime());
                 tr.fo = r.o;
                 tr.fd = r.d;
                 tr.f_nops = fr.y;
@@ -942,7 +970,7 @@ RT_HD bool shade_and_scatter(const SceneT<Mem, kFeat>& sc, const KParams& P, Pat
     V3 lo = st.ro, ld = st.rd;
     if ((kFeat & SF_WRAP) && frame != 0u) {
         fr = sc.frame(frame);
-        const Ray6 r = frame_ops_ray(sc.m, sc.off_ops + 16u * fr.x, fr.y, lo, ld, st.rtime);
+        const Ray6 r = frame_ops_ray<kFeat>(sc.m, sc.off_ops + 16u * fr.x, fr.y, lo, ld, st.rtime);
         lo = r.o;
         ld = r.d;
     }
@@ -965,7 +993,7 @@ RT_HD bool shade_and_scatter(const SceneT<Mem, kFeat>& sc, const KParams& P, Pat
         n = mk(1.f, 0.f, 0.f);
     }
     if ((kFeat & SF_WRAP) && fr.y != 0u) {
-        const Ray6 r = frame_ops_hit(sc.m, sc.off_ops + 16u * fr.x, fr.y, p, n);
+        const Ray6 r = frame_ops_hit<kFeat>(sc.m, sc.off_ops + 16u * fr.x, fr.y, p, n);
         p = r.o;
         n = r.d;
     }

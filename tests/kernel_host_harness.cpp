@@ -27,7 +27,7 @@ static int harness_render_impl(const rtiow_scene_desc_t* desc, const rtiow_camer
     if (int rc = validate_desc(desc, &has_frames, &uses_perlin, &msg)) return rc;
     BlobLayout lay{};
     const std::vector<unsigned char> blob = build_blob(desc, uses_perlin, &lay, accel == 1 ? kBlobFast : (accel == 2 ? kBlobExact : kBlobReferenceOrder), g_fuse_prisms);
-    if (layout_out) { layout_out[0] = lay.n_items; layout_out[1] = lay.n_nodes; layout_out[2] = lay.n_accel; layout_out[3] = lay.accel_depth; layout_out[5] = lay.n_prisms; layout_out[6] = static_cast<uint32_t>(blob.size()); layout_out[7] = lay.n_ordered; }
+    if (layout_out) { layout_out[0] = lay.n_items; layout_out[1] = lay.n_nodes; layout_out[2] = lay.n_accel; layout_out[3] = lay.accel_depth; layout_out[5] = lay.n_prisms; layout_out[6] = static_cast<uint32_t>(blob.size()); layout_out[7] = lay.n_ordered; layout_out[8] = lay.n_derived; }
     KParams P{};
     P.blob = blob.data();
     P.blob_bytes = static_cast<uint32_t>(blob.size());
@@ -92,13 +92,16 @@ extern "C" __attribute__((visibility("default"))) int harness_render(const rtiow
         if (int rc = rtiow::validate_desc(desc, &has_frames, &uses_perlin, &msg)) return rc;
         rtiow::BlobLayout lay{};
         rtiow::build_blob(desc, uses_perlin, &lay, accel == 1 ? rtiow::kBlobFast : (accel == 2 ? rtiow::kBlobExact : rtiow::kBlobReferenceOrder));
-        const uint32_t needs = rtiow::scene_features(desc) | (lay.n_accel ? static_cast<uint32_t>(rtiow::SF_ACCEL) : 0u);
+        const uint32_t needs = rtiow::scene_features(desc) | (lay.n_accel ? static_cast<uint32_t>(rtiow::SF_ACCEL) : 0u) |
+                               (lay.n_ordered ? static_cast<uint32_t>(rtiow::SF_ORDERED) : 0u);
         if (!has_frames && (needs & ~rtiow::kFeatSpheres) == 0u) profile = 1;
         else if (!has_frames && (needs & ~rtiow::kFeatRects) == 0u) profile = 2;
+        else if ((needs & ~rtiow::kFeatLean) == 0u) profile = 3;
     }
     if (layout_out) layout_out[4] = profile;
     if (profile == 1) return harness_render_impl<rtiow::kFeatSpheres>(desc, cam, nx, ny, ns, seed, row_begin, row_end, out_rgb, out_samples, accel, layout_out, row_step, row_band);
     if (profile == 2) return harness_render_impl<rtiow::kFeatRects>(desc, cam, nx, ny, ns, seed, row_begin, row_end, out_rgb, out_samples, accel, layout_out, row_step, row_band);
+    if (profile == 3) return harness_render_impl<rtiow::kFeatLean>(desc, cam, nx, ny, ns, seed, row_begin, row_end, out_rgb, out_samples, accel, layout_out, row_step, row_band);
     return harness_render_impl<rtiow::SF_ALL>(desc, cam, nx, ny, ns, seed, row_begin, row_end, out_rgb, out_samples, accel, layout_out, row_step, row_band);
 }
 
@@ -138,7 +141,7 @@ extern "C" __attribute__((visibility("default"))) int harness_trace_rays(const r
             const float4 a = sc.item_a(best & kItemMask), b = sc.item_b(best & kItemMask);
             uint32_t h = 2166136261u;
             const bool medium = (f2u(a.w) & 15u) == IT_MEDIUM;  // a[2] of a medium is an item index: differs between blobs
-            const uint32_t w[8] = {f2u(a.x), f2u(a.y), medium ? 0u : f2u(a.z), f2u(a.w) & 15u, f2u(b.x), f2u(b.y), f2u(b.z), f2u(b.w) | (best & ~kItemMask)};
+            const uint32_t w[8] = {f2u(a.x), f2u(a.y), medium ? 0u : f2u(a.z), f2u(a.w) & 15u, f2u(b.x), f2u(b.y), f2u(b.z), (f2u(b.w) & ~(FL_BOX_DERIVED << 24)) | (best & ~kItemMask)};  // the library's own flag differs between blobs
             for (uint32_t k = 0; k < 8; ++k) h = (h ^ w[k]) * 16777619u;
             id = h & 0x7fffffffu;
         }

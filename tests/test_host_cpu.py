@@ -208,14 +208,14 @@ def test_reindexed_subtrees_layout():
     on the reference-order stream."""
     def layout(name, bvh, accel=2):
         world, cam = R.build_scene(name, 8, 8, use_bvh=bvh)
-        lay = np.zeros(8, np.uint32)
+        lay = np.zeros(10, np.uint32)
         H.render(world, cam, 8, 8, 1, accel=accel, layout=lay)
         return world.counts(), dict(items=int(lay[0]), nodes=int(lay[1]), accels=int(lay[2]), depth=int(lay[3])), int(lay[5])
     c, l, _ = layout("book1", True)
     assert l["accels"] == 1 and l["nodes"] == c["spheres"] - 2            # one leaf per sphere; the ground sphere stays outside
     assert l["items"] == c["spheres"] + 3 and l["depth"] <= 30            # ACCEL + spheres + the ordered leaf's BBOX + END
-    c, l, _ = layout("book1", True, accel=1)                              # fast tree: each leaf keeps its own BBOX item
-    assert l["accels"] == 1 and l["items"] == 2 * c["spheres"] + 2
+    c, l, _ = layout("book1", True, accel=1)                              # fast tree: a leaf's box is derived from its sphere's
+    assert l["accels"] == 1 and l["items"] == c["spheres"] + 3            # record, so no BBOX item is kept except the ordered leaf's
     c, l, prisms = layout("book1", True, accel=0)
     assert l == dict(items=c["items"], nodes=0, accels=0, depth=0) and prisms == 0   # the stream as flattened
     c, l, _ = layout("book1", False)
@@ -288,7 +288,7 @@ def test_ordered_leaves_keep_order_dependent_hits(oracle):
     every traversal gives the oracle's bits."""
     nx, ny, ns = 400, 200, 50
     world, cam = R.build_scene("book1", nx, ny)
-    lay = np.zeros(8, np.uint32)
+    lay = np.zeros(10, np.uint32)
     H.render(world, cam, 8, 8, 1, accel=1, layout=lay)
     assert lay[7] == 1                                                   # exactly one ordered leaf: the ground
     want, osmp, _ = oracle.Scene("book1", nx, ny).render(ns, nthreads=4, rows=(89, 90), want_samples=True)
@@ -392,9 +392,10 @@ def test_feature_specialisations_match_the_general_code(oracle):
     the same bits as the general code."""
     nx, ny, ns = 48, 32, 6
     for name, bvh, profile in (("book1", True, 1), ("book1", False, 1), ("cornell", False, 2), ("cornell_empty", False, 2),
-                               ("bench_cornell", True, 0), ("kitchen_sink", True, 0), ("final", False, 0), ("volume_test", False, 0)):
+                               ("bench_cornell", True, 3), ("kitchen_sink", True, 0), ("final", False, 3), ("final", True, 3),
+                               ("volume_test", False, 3), ("cornell_smoke", False, 0), ("simple_light", True, 0)):   # simple_light: an ordered leaf (the radius-1000 light)
         world, cam = R.build_scene(name, nx, ny, use_bvh=bvh)
-        lay = np.zeros(8, np.uint32)
+        lay = np.zeros(10, np.uint32)
         general, gs = H.render(world, cam, nx, ny, ns, want_samples=True, accel=1)
         special, ss = H.render(world, cam, nx, ny, ns, want_samples=True, accel=1, lean=True, layout=lay)
         assert int(lay[4]) == profile, (name, int(lay[4]))
