@@ -190,7 +190,8 @@ typedef struct rtiow_stats_t {
     uint32_t accel_subtrees; /* how many Bvh subtrees were re-indexed                                      */
     uint32_t traversal;      /* RTIOW_TRAVERSAL_*: how the last render walked Bvh subtrees                 */
     uint32_t kernel_profile; /* which compilation of the megakernel the last render used: 0 general, 1 spheres-only
-                                scenes, 2 rect-list scenes (rtiow_b200_set_specialisation)                  */
+                                scenes, 2 rect-list scenes, 3 general minus the features none of the reference's own
+                                scenes builds (rtiow_b200_set_specialisation)                               */
 } rtiow_stats_t;
 
 typedef struct rtiow_scene rtiow_scene_t;
@@ -308,11 +309,12 @@ RTIOW_API int rtiow_b200_get_stats(rtiow_scene_t* scene, rtiow_stats_t* out);
 RTIOW_API int rtiow_b200_set_tuning(rtiow_scene_t* scene, uint32_t cta_threads, uint32_t ctas_per_sm, uint32_t staging_mib,
                           int force_global);
 
-/* The megakernel is compiled for three feature sets: any scene; scenes that hold nothing but unwrapped spheres
- * with Lambertian / Metal / Dielectric materials and constant textures (book-1's random_scene); and lists of
- * rects, wrapped or not, with Lambertian and DiffuseLight materials (the Cornell box) — the same per-path code
- * with everything else compiled out: half the instructions, no register spills.  Picked automatically from the
- * scene's content; enable = 0 forces the general kernel.  Same image either way. */
+/* The megakernel is compiled for four feature sets: any scene; scenes that hold nothing but unwrapped spheres
+ * with Lambertian / Metal / Dielectric materials and constant textures (book-1's random_scene); lists of rects and
+ * rect_prisms, wrapped or not, with Lambertian and DiffuseLight materials (the Cornell box); and any scene without a
+ * multi-item ConstantMedium boundary, a checker texture or a Scale wrapper (the book-2 final scene) — the same
+ * per-path code with everything else compiled out: the kernel is bound by instruction fetch, so code that never runs
+ * still costs.  Picked automatically from the scene's content; enable = 0 forces the general kernel.  Same image. */
 RTIOW_API int rtiow_b200_set_specialisation(rtiow_scene_t* scene, int enable);
 
 /* How `Bvh` subtrees (src/bvh.rs) are walked.  All give the same image bit for bit; the choice is
