@@ -57,9 +57,19 @@ struct DevBuf {
 // (one per frame in a host application) do not pay cudaMalloc/cudaFree of the sample staging buffer.
 struct Workspace {
     int device = 0;
-    DevBuf staging, accum, out, samples;
+    // Two pipeline slots (staging, pass accumulator, unit counter, a stream for the megakernel): consecutive renders
+    // alternate between them, so that render k+1's CTAs move onto the SMs that render k's CTAs leave while its last
+    // long paths are still running (enqueue_render).  Frames whose staging is large use slot 0 only.
+    struct Slot {
+        DevBuf staging, accum;
+        unsigned int* d_counter = nullptr;
+        cudaStream_t stream = nullptr;
+        cudaEvent_t render_done = nullptr, fold_done = nullptr;
+        bool fold_recorded = false;
+    } slot[2];
+    uint32_t next_slot = 0;
+    DevBuf out, samples;
     DevBuf scene_blob[3];  // device image of the owning scene, by blob mode
-    unsigned int* d_counter = nullptr;
     unsigned long long* d_segs = nullptr;
     cudaStream_t stream = nullptr;
     std::vector<cudaEvent_t> events;  // [start, trace_end, fold_end] per pass
@@ -88,13 +98,20 @@ struct Workspace {
     void wait_idle() {
         if (busy_recorded) cudaEventSynchronize(busy);
         if (stream) cudaStreamSynchronize(stream);
+        for (Slot& sl : slot)
+            if (sl.stream) cudaStreamSynchronize(sl.stream);
     }
 
     cudaError_t init(int dev) {
         device = dev;
         cudaError_t e;
         if ((e = cudaEventCreateWithFlags(&busy, cudaEventDisableTiming)) != cudaSuccess) return e;
-        if ((e = cudaMalloc(reinterpret_cast<void**>(&d_counter), sizeof(unsigned int))) != cudaSuccess) return e;
+        for (Slot& sl : slot) {
+            if ((e = cudaMalloc(reinterpret_cast<void**>(&sl.d_counter), sizeof(unsigned int))) != cudaSuccess) return e;
+            if ((e = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&sl.render_done, cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&sl.fold_done, cudaEventDisableTiming)) != cudaSuccess) return e;
+        }
         if ((e = cudaMalloc(reinterpret_cast<void**>(&d_segs), sizeof(unsigned long long))) != cudaSuccess) return e;
         if ((e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
         return cudaSuccess;
@@ -103,9 +120,16 @@ struct Workspace {
         cudaSetDevice(device);
         wait_idle();
         if (busy) cudaEventDestroy(busy);
-        staging.release(); accum.release(); out.release(); samples.release();
+        for (Slot& sl : slot) {
+            if (sl.stream) cudaStreamSynchronize(sl.stream);
+            sl.staging.release(); sl.accum.release();
+            if (sl.d_counter) cudaFree(sl.d_counter);
+            if (sl.render_done) cudaEventDestroy(sl.render_done);
+            if (sl.fold_done) cudaEventDestroy(sl.fold_done);
+            if (sl.stream) cudaStreamDestroy(sl.stream);
+        }
+        out.release(); samples.release();
         for (DevBuf& b : scene_blob) b.release();
-        if (d_counter) cudaFree(d_counter);
         if (d_segs) cudaFree(d_segs);
         for (cudaEvent_t ev : events) cudaEventDestroy(ev);
         for (int i = 0; i < 2; ++i) {
@@ -306,6 +330,7 @@ struct rtiow_scene {
     bool specialise = true;        // use a kernel compiled for a subset of features when the scene allows (same image)
     uint32_t refill_lanes = 0;     // 0 = automatic
     bool costly_segments = false;  // the scene has wrapper frames on subtrees or constant media
+    bool pipeline = true;          // consecutive renders alternate between two pipeline slots (RTIOW_B200_PIPELINE=0: one)
     bool fuse_prisms = true;       // six-Rect rect_prism runs become one prism record (RTIOW_B200_FUSE_PRISMS=0: keep the rects)
     bool bottom_first = true;      // unit order (RTIOW_B200_UNIT_ORDER=0: top rows first)
     int phase_sync = -1;           // -1 = automatic (RTIOW_B200_PHASE_SYNC, read once at scene_create)
@@ -388,21 +413,30 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     CK(W.order_after_last_render(stream));
     // Per-sample staging budget.  Automatic: up to 56 GiB, at most 70 % of what is free — a B200 has 180 GB and a
     // pass boundary costs a kernel tail, so C3 (10 GB), C4 (51 GB) and one rank's share of C5 (15 GB) are single passes.
+    // Which pipeline slot: alternate for frames whose staging is small (a kernel of a few milliseconds, where the ~0.15 ms
+    // in which the last long paths finish is worth hiding behind the next render); big frames stay on slot 0.
+    const bool pipelined = s->pipeline && npix64 * ns * 16 <= (4ull << 30);
+    const uint32_t slot_id = pipelined ? (W.next_slot++ & 1u) : 0u;
+    Workspace::Slot& SL = W.slot[slot_id];
     uint64_t budget = static_cast<uint64_t>(s->staging_mib) << 20;
-    if (s->staging_mib == 0 && npix64 * ns * 16 <= W.staging.cap) {
-        budget = W.staging.cap;  // the whole frame fits what is already there: no need to ask the driver (cudaMemGetInfo is slow)
+    if (s->staging_mib == 0 && npix64 * ns * 16 <= SL.staging.cap) {
+        budget = SL.staging.cap;  // the whole frame fits what is already there: no need to ask the driver (cudaMemGetInfo is slow)
     } else if (s->staging_mib == 0) {
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
-        budget = std::min<uint64_t>(56ull << 30, (static_cast<uint64_t>(free_b) + W.staging.cap) / 10 * 7);
+        budget = std::min<uint64_t>(56ull << 30, (static_cast<uint64_t>(free_b) + SL.staging.cap) / 10 * 7);
         budget = std::max<uint64_t>(budget, 64ull << 20);
     }
     // passes of equal size (the last one is not a sliver)
     const uint32_t s_max = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(ns, budget / (npix64 * 16))));
     const uint32_t n_pass = (ns + s_max - 1) / s_max;
     const uint32_t s_pass = (ns + n_pass - 1) / n_pass;
-    CK(W.staging.reserve(npix64 * s_pass * 16));
-    CK(W.accum.reserve(npix64 * 16));
+    if (npix64 * s_pass * 16 > SL.staging.cap || npix64 * 16 > SL.accum.cap) {
+        CK(cudaStreamSynchronize(SL.stream));  // the buffers are about to be replaced
+        if (SL.fold_recorded) CK(cudaEventSynchronize(SL.fold_done));
+    }
+    CK(SL.staging.reserve(npix64 * s_pass * 16));
+    CK(SL.accum.reserve(npix64 * 16));
 
     // ---- which blob: REINDEXED means the conservative-test tree when it fits in shared memory, else the
     // exact-test tree (smaller) when that fits, else the conservative-test tree from global memory
@@ -468,8 +502,8 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     P.key0 = static_cast<uint32_t>(seed); P.key1 = static_cast<uint32_t>(seed >> 32);
     P.bg_kind = s->bg_kind;
     std::memcpy(P.bg0, s->bg0, 12); std::memcpy(P.bg1, s->bg1, 12);
-    P.staging = static_cast<float4*>(W.staging.p);
-    P.work_counter = W.d_counter;
+    P.staging = static_cast<float4*>(SL.staging.p);
+    P.work_counter = SL.d_counter;
     // Scenes whose segments run through a lot of different code (media, wrapper frames, nested subtrees) are
     // bound by instruction fetch: ncu shows `no_instruction` as the top stall with the 99 % hot set at 35 KB against
     // a 32 KB L1.5 I-cache.  Two CTA barriers per round (before hit_top, before shading) keep the 24 warps in the
@@ -489,35 +523,80 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     P.refill_thr = s->refill_lanes ? s->refill_lanes : (s->costly_segments ? 1u : (s->bg_kind == RTIOW_BG_SKY_GRADIENT ? 12u : 4u));
 
     P.bottom_first = s->bottom_first ? 1u : 0u;
-    // Work unit = s_chunk samples of one tile.  The kernel ends when the last warp finishes its last unit, so
-    // a unit must be a small fraction of a warp's share: the largest chunk of 8, 4, 2, 1 that still leaves
-    // every resident warp ~48 units (one GPU at C2: 8; an eighth of the frame on each of 8 GPUs: 1).
-    uint32_t chunk_pref = s->sample_chunk;
-    if (chunk_pref == 0) {
-        const uint64_t want_units = 48ull * grid * warps_per_cta;
-        chunk_pref = 8u;
-        while (chunk_pref > 1u && static_cast<uint64_t>(n_groups) * ((std::min(s_pass, ns) + chunk_pref - 1) / chunk_pref) < want_units)
-            chunk_pref >>= 1;
-    }
-    if (int rc = ensure_events(s, 1 + 2 * n_pass)) return rc;
+    // Work units (KParams): chunks of 8 samples of a tile while there is plenty of work — one atomic, one coherent batch
+    // of camera rays per 256 samples — and small chunks for the last fifth or so, because the kernel ends when the last
+    // warp finishes its last unit.  Sized so that every resident warp gets >= 8 of the small units (one GPU at C2: 8 + 2;
+    // an eighth of the frame on each of 8 GPUs: 8 + 1).  Round 1 used ONE size, 1 sample per unit on 8 GPUs: the kernel
+    // lost 17 % against T(1)/8 there, most of it per-unit overhead and incoherent refills rather than tail.
+    const uint64_t resident_warps = static_cast<uint64_t>(grid) * warps_per_cta;
+    auto plan_units = [&](uint32_t s_count, KParams& K) {
+        K.n_groups = n_groups;
+        if (s->sample_chunk != 0u) {  // forced single size
+            K.s_chunk = std::min(s->sample_chunk, s_count);
+            K.s_tail_begin = s_count;
+        } else if (s->bg_kind == RTIOW_BG_SKY_GRADIENT) {
+            // open scenes (most units are cheap sky): ONE size, the largest of 8, 4, 2, 1 that leaves every resident warp ~48
+            // units — measured on book-1: 10.68 ms against 10.97 ms with a tail of smaller units; closed scenes (Cornell:
+            // every path is long) gain 3 % from the tail instead
+            uint32_t c = 8u;
+            while (c > 1u && static_cast<uint64_t>(n_groups) * ((s_count + c - 1) / c) < 48ull * resident_warps) c >>= 1;
+            K.s_chunk = std::min(c, s_count);
+            K.s_tail_begin = s_count;
+        } else {
+            // big chunks: the largest of 8, 4, 2, 1 of which every resident warp still gets >= 24 (a unit must stay a
+            // small fraction of a warp's share: with 3 units of 8 per warp, 8 GPUs lost 25 % to the unlucky warps)
+            const uint32_t body = s_count - (s_count + 4u) / 5u;
+            uint32_t big = 8u;
+            while (big > 1u && static_cast<uint64_t>(n_groups) * (body / big) < 24ull * resident_warps) big >>= 1;
+            K.s_chunk = std::min(big, s_count);
+            // the tail: about a fifth of the samples in chunks of at most half that size, >= 8 per warp
+            const uint64_t want_tail_units = 8ull * resident_warps;
+            uint32_t tail = (s_count + 4u) / 5u;
+            uint32_t small = std::max(1u, K.s_chunk / 2u);
+            while (small > 1u && static_cast<uint64_t>(n_groups) * (tail / small) < want_tail_units) small >>= 1;
+            uint32_t big_samples = (s_count - tail) / K.s_chunk * K.s_chunk;  // whole big chunks
+            if (K.s_chunk == 1u) big_samples = s_count;                        // nothing smaller to end with
+            K.s_tail_begin = big_samples;
+            K.s_chunk_tail = small;
+        }
+        K.n_chunks = K.s_tail_begin / std::max(1u, K.s_chunk) + (K.s_tail_begin % std::max(1u, K.s_chunk) ? 1u : 0u);
+        if (K.s_tail_begin == s_count) {
+            K.n_chunks = (s_count + K.s_chunk - 1) / K.s_chunk;
+            K.s_chunk_tail = 1u;
+            K.n_chunks_tail = 0u;
+        } else {
+            K.n_chunks_tail = (s_count - K.s_tail_begin + K.s_chunk_tail - 1) / K.s_chunk_tail;
+        }
+        if (static_cast<uint64_t>(n_groups) * (K.n_chunks + K.n_chunks_tail) >= (1ull << 32)) {  // keep the unit counter in 32 bits
+            K.s_chunk = s_count; K.n_chunks = 1; K.s_tail_begin = s_count; K.n_chunks_tail = 0; K.s_chunk_tail = 1;
+        }
+        K.n_big_units = n_groups * K.n_chunks;
+        K.n_units = K.n_big_units + n_groups * K.n_chunks_tail;
+    };
+    // The megakernel runs on the slot's own stream, everything that consumes its samples (export, fold, the peers'
+    // hand-shake) on the caller's.  Dependencies: a render needs the previous fold of ITS slot (the staging buffer and the
+    // pass accumulator are reused) and nothing of the caller's stream — its inputs are the scene and this call's arguments;
+    // a fold needs its render.  So with two slots render k+1 is released while render k is still running: one persistent CTA
+    // fills an SM's register file, so k+1's CTAs start exactly where k's have finished — the time in which k's last long
+    // paths (up to 51 segments each, ~0.15 ms on book-1 whatever the frame size) keep a few SMs busy is no longer idle time
+    // on the others.  Same image: nothing about a render depends on when it runs.
+    if (int rc = ensure_events(s, 4 * n_pass)) return rc;
     s->events_used = 0;
     CK(cudaMemsetAsync(W.d_segs, 0, sizeof(unsigned long long), stream));
-    CK(cudaEventRecord(W.events[s->events_used++], stream));
     uint32_t launches = 0;
     for (uint32_t pass = 0; pass < n_pass; ++pass) {
         P.s_begin = pass * s_pass;
         P.s_count = std::min(s_pass, ns - P.s_begin);
-        P.s_chunk = std::min(chunk_pref, P.s_count);
-        P.n_chunks = (P.s_count + P.s_chunk - 1) / P.s_chunk;
-        if (static_cast<uint64_t>(n_groups) * P.n_chunks >= (1ull << 32)) {  // keep the unit counter in 32 bits
-            P.s_chunk = P.s_count;
-            P.n_chunks = 1;
-        }
-        P.n_units = n_groups * P.n_chunks;
-        CK(cudaMemsetAsync(W.d_counter, 0, sizeof(unsigned int), stream));
-        var.fn<<<grid, var.threads, dyn_smem, stream>>>(P);
+        plan_units(P.s_count, P);
+        if (SL.fold_recorded) CK(cudaStreamWaitEvent(SL.stream, SL.fold_done, 0));
+        CK(cudaMemsetAsync(SL.d_counter, 0, sizeof(unsigned int), SL.stream));
+        CK(cudaEventRecord(W.events[s->events_used++], SL.stream));
+        var.fn<<<grid, var.threads, dyn_smem, SL.stream>>>(P);
         CK(cudaGetLastError());
         ++launches;
+        CK(cudaEventRecord(W.events[s->events_used++], SL.stream));
+        CK(cudaEventRecord(SL.render_done, SL.stream));
+        CK(cudaStreamWaitEvent(stream, SL.render_done, 0));
         CK(cudaEventRecord(W.events[s->events_used++], stream));
         if (d_samples) {
             const uint64_t n = npix64 * P.s_count;
@@ -545,12 +624,14 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
                 dst.n = 1u;
             }
             rtiow::fold_kernel<<<(npix + 255u) / 256u, 256, 0, stream>>>(
-                P.staging, static_cast<float4*>(W.accum.p), dst, npix, P.s_count, pass == 0, pass + 1 == n_pass,
+                P.staging, static_cast<float4*>(SL.accum.p), dst, npix, P.s_count, pass == 0, pass + 1 == n_pass,
                 static_cast<float>(ns), W.d_segs);
             CK(cudaGetLastError());
             ++launches;
         }
         CK(cudaEventRecord(W.events[s->events_used++], stream));
+        CK(cudaEventRecord(SL.fold_done, stream));
+        SL.fold_recorded = true;
     }
     CK(W.mark_render_end(stream));
     s->stats = rtiow_stats_t{};
@@ -643,6 +724,7 @@ int rtiow_b200_scene_create(const rtiow_scene_desc_t* d, int device, rtiow_scene
     if (const char* env = std::getenv("RTIOW_B200_TRAVERSAL")) s->traversal = std::min(2, std::max(0, std::atoi(env)));
     if (const char* env = std::getenv("RTIOW_B200_SPECIALISE")) s->specialise = std::atoi(env) != 0;
     if (const char* env = std::getenv("RTIOW_B200_REFILL_LANES")) s->refill_lanes = static_cast<uint32_t>(std::min(32, std::max(0, std::atoi(env))));
+    if (const char* env = std::getenv("RTIOW_B200_PIPELINE")) s->pipeline = std::atoi(env) != 0;
     if (const char* env = std::getenv("RTIOW_B200_FUSE_PRISMS")) s->fuse_prisms = std::atoi(env) != 0;
     if (const char* env = std::getenv("RTIOW_B200_UNIT_ORDER")) s->bottom_first = std::atoi(env) != 0;
     if (const char* env = std::getenv("RTIOW_B200_PHASE_SYNC")) s->phase_sync = std::max(0, std::atoi(env));
@@ -1060,10 +1142,10 @@ int rtiow_b200_get_stats(rtiow_scene_t* s, rtiow_stats_t* out) {
     CK(cudaSetDevice(s->device));
     CK(cudaDeviceSynchronize());
     double trace = 0, fold = 0;
-    for (uint32_t i = 0; i + 2 < s->events_used; i += 2) {  // [start, (trace_end, fold_end) per pass]
+    for (uint32_t i = 0; i + 4 <= s->events_used; i += 4) {  // per pass: render start/end, fold start/end
         float a = 0, b = 0;
         CK(cudaEventElapsedTime(&a, s->ws->events[i], s->ws->events[i + 1]));
-        CK(cudaEventElapsedTime(&b, s->ws->events[i + 1], s->ws->events[i + 2]));
+        CK(cudaEventElapsedTime(&b, s->ws->events[i + 2], s->ws->events[i + 3]));
         trace += a;
         fold += b;
     }

@@ -42,7 +42,12 @@ struct KParams {
     uint32_t nx, ny, row_begin, n_rows, row_step, row_band;
     uint32_t s_begin, s_count;  // samples [s_begin, s_begin + s_count) of every pixel in this pass
     uint32_t npix, tiles_x;     // the row block is cut into 8x4-pixel tiles, tiles_x per tile row
-    uint32_t s_chunk, n_chunks, n_units;  // work unit = s_chunk samples of one tile
+    // Work unit = a chunk of samples of one tile, in two sizes: units [0, n_big_units) are chunks of s_chunk samples
+    // covering samples [0, s_tail_begin) of every tile, the rest chunks of s_chunk_tail samples covering the remainder —
+    // large units while there is plenty of work (one atomic and one coherent batch of rays per 8 x 32 samples), small ones
+    // for the end, because the kernel ends when the last warp finishes its last unit.
+    uint32_t s_chunk, n_chunks, n_units;
+    uint32_t s_chunk_tail, n_chunks_tail, n_big_units, s_tail_begin, n_groups;
     uint32_t key0, key1;
     uint32_t bg_kind;
     float bg0[3], bg1[3];
@@ -66,6 +71,7 @@ struct MemPtr {  // generic pointer: host harness
     RT_HD uint2 ld2(uint32_t off) const { return *reinterpret_cast<const uint2*>(base + off); }
     RT_HD uint32_t ld1b(uint32_t off) const { return base[off]; }
 };
+
 #ifdef __CUDACC__
 struct MemShared {
     uint32_t base;  // shared-window address of the staged blob

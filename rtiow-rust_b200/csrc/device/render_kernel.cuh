@@ -120,16 +120,24 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
                 if (lane == 0) u = atomicAdd(P.work_counter, 1u);
                 u = __shfl_sync(0xffffffffu, u, 0);
                 if (u >= P.n_units) { exhausted = true; break; }
-                // unit u = samples [c * s_chunk, ...) of tile g; small units keep the tail short.  Tiles are handed out
+                // unit u = a chunk of samples of tile g (KParams: two chunk sizes).  Tiles are handed out
                 // from the BOTTOM of the row block: the kernel ends when the last warp finishes its last unit, and in the
                 // reference's scenes the cheap pixels (sky, one segment) are at the top — they make the better tail.
-                if (P.bottom_first != 0u) u = P.n_units - 1u - u;
-                const uint32_t g = u / P.n_chunks, c = u - g * P.n_chunks;
+                uint32_t g, s_n;
+                if (u < P.n_big_units) {
+                    g = u / P.n_chunks;
+                    pool_s0 = (u - g * P.n_chunks) * P.s_chunk;
+                    s_n = P.s_tail_begin - pool_s0 < P.s_chunk ? P.s_tail_begin - pool_s0 : P.s_chunk;
+                } else {
+                    const uint32_t v = u - P.n_big_units;
+                    g = v / P.n_chunks_tail;
+                    pool_s0 = P.s_tail_begin + (v - g * P.n_chunks_tail) * P.s_chunk_tail;
+                    s_n = P.s_count - pool_s0 < P.s_chunk_tail ? P.s_count - pool_s0 : P.s_chunk_tail;
+                }
+                if (P.bottom_first != 0u) g = P.n_groups - 1u - g;
                 const uint32_t ty = g / P.tiles_x;
                 pool_x0 = (g - ty * P.tiles_x) * kTileW;
                 pool_r0 = ty * kTileH;
-                pool_s0 = c * P.s_chunk;
-                const uint32_t s_n = P.s_count - pool_s0 < P.s_chunk ? P.s_count - pool_s0 : P.s_chunk;
                 pool_next = 0u;
                 pool_end = 32u * s_n;
             }
