@@ -513,8 +513,8 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     P.phase_group = static_cast<uint32_t>(var.threads) / 32u;
     if (P.phase_sync != 0u && P.phase_group % 2u == 0u) P.phase_group /= 2u;  // two barrier groups per CTA: measured best
     if (s->phase_group_env) {
-        const uint32_t g = s->phase_group_env;
-        if (P.phase_group % g == 0 && P.phase_group / g <= 15) P.phase_group = g;
+        const uint32_t g = s->phase_group_env, warps = static_cast<uint32_t>(var.threads) / 32u;
+        if (warps % g == 0 && warps / g <= 15) P.phase_group = g;
     }
     // Idle lanes get new pixel-samples once `refill_thr` lanes of the warp wait: generating camera rays costs the
     // warp the same for 3 lanes as for 30, and rays started together stay coherent.  Waiting costs idle lane

@@ -5,13 +5,30 @@ cat > /tmp/san.py <<'PY'
 import sys, os
 sys.path.insert(0, os.getcwd())
 import rtiow_rust_b200 as R
-for name, nx, ny, ns, bvh in (("book1", 64, 48, 4, True), ("cornell", 32, 32, 4, False), ("final", 32, 32, 4, False), ("kitchen_sink", 32, 32, 4, True)):
+import torch
+from rtiow_rust_b200 import dist as rdist
+for name, nx, ny, ns, bvh in (("book1", 64, 48, 4, True), ("cornell", 32, 32, 4, False), ("final", 32, 32, 4, False), ("kitchen_sink", 32, 32, 4, True),
+                              ("cornell_smoke", 32, 32, 4, False), ("simple_light", 32, 32, 2, True)):
     w, c = R.build_scene(name, nx, ny, use_bvh=bvh)
     for trav in (0, 2, 1):
         w.set_traversal(trav)
-        img = R.par_cast(nx, ny, ns, c, w).rgb
-    print(name, "ok", float(img.mean()))
+        img = R.par_cast(nx, ny, ns, c, w).rgb          # consecutive renders alternate between the two pipeline slots
+    q = R.par_cast_ppm(nx, ny, ns, c, w)
+    print(name, "ok", float(img.mean()), int(q.sum()))
     w.close()
+# the multi-GPU exchange with both ranks on this GPU: fold stores into two frames, flag hand-shake
+nx, ny, ns = 64, 48, 3
+worlds = [R.build_scene("book1", nx, ny) for _ in range(2)]
+frames = [rdist.PeerFrame(worlds[r][0].lib, nx, ny, 0, r, 2, connect=False) for r in range(2)]
+for f in frames:
+    f.connect([g.handle for g in frames])
+streams = [torch.cuda.Stream() for _ in range(2)]
+for rep in range(3):
+    for r in range(2):
+        frames[r].render(nx, ny, ns, worlds[r][1], worlds[r][0], 1, stream=streams[r])
+    for st in streams:
+        st.synchronize()
+print("peers ok", float(frames[0].frame.mean()), bool((frames[0].frame == frames[1].frame).all()))
 PY
 for tool in memcheck racecheck; do
   timeout 900 compute-sanitizer --tool $tool --print-limit 5 python /tmp/san.py > gpurun_out/sanitizer_$tool.log 2>&1

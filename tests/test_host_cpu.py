@@ -38,6 +38,17 @@ def test_abi_library_exports_every_declared_symbol():
         assert exported == declared, exported ^ declared       # nothing else leaks out of the library
 
 
+def test_header_is_plain_c_and_links(tmp_path):
+    """The header as a C11 translation unit (-Wall -Wextra -Werror -pedantic) linked against the shipped library: what a
+    cgo / bindgen / JNI binding would read.  Runs the GPU-free entry points on a hand-written one-sphere descriptor."""
+    exe = str(tmp_path / "abi_smoke")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-o", exe,
+                           os.path.join(ROOT, "tests", "c_abi", "abi_smoke.c"), "-L" + N.BUILD_DIR, "-lrtiow_b200",
+                           "-Wl,-rpath," + N.BUILD_DIR])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "abi_smoke ok" in out.stdout, (out.returncode, out.stdout, out.stderr)
+
+
 def test_abi_struct_sizes_match_header():
     assert C.sizeof(N.Item) == 32 and C.sizeof(N.XformOp) == 16 and C.sizeof(N.Frame) == 8
     assert C.sizeof(N.MaterialRec) == 32 and C.sizeof(N.TextureRec) == 32 and C.sizeof(N.CameraRec) == 84
