@@ -274,12 +274,27 @@ RT_HD bool rect_hit_axis(float oa, float da, float o1, float d1, float o2, float
     t_out = t;
     return true;
 }
+// RT_RECT_OUTLINE (set by the translation unit of the lean general kernel, which is bound by instruction fetch): ONE
+// out-of-line copy of the rect test, components picked by selects, instead of three axis variants at each of three call
+// sites.  Rects are rare in the scenes that kernel renders; their code was 7 % of it.  Final scene 83.6 -> 82.6 ms / 100 spp.
+#ifndef RT_RECT_OUTLINE
+#define RT_RECT_OUTLINE 0
+#endif
+#if RT_RECT_OUTLINE
+static RT_HD_NOINLINE bool rect_hit_t(V3 o, V3 d, uint32_t axis, float4 ia, float4 ib, float t_lo, float t_hi, float& t_out) {
+    const float oa = axis == 0u ? o.x : (axis == 1u ? o.y : o.z), da = axis == 0u ? d.x : (axis == 1u ? d.y : d.z);
+    const float o1 = axis == 0u ? o.y : o.x, d1 = axis == 0u ? d.y : d.x;  // "other two" alphabetical (object.rs:153-181)
+    const float o2 = axis == 2u ? o.y : o.z, d2 = axis == 2u ? d.y : d.z;
+    return rect_hit_axis(oa, da, o1, d1, o2, d2, ia, ib, t_lo, t_hi, t_out);
+}
+#else
 RT_HD bool rect_hit_t(V3 o, V3 d, uint32_t axis, float4 ia, float4 ib, float t_lo, float t_hi, float& t_out) {
     // lanes of a warp walk the same item list, so `axis` is uniform in practice: a branch, not selects
     if (axis == 0u) return rect_hit_axis(o.x, d.x, o.y, d.y, o.z, d.z, ia, ib, t_lo, t_hi, t_out);
     if (axis == 1u) return rect_hit_axis(o.y, d.y, o.x, d.x, o.z, d.z, ia, ib, t_lo, t_hi, t_out);
     return rect_hit_axis(o.z, d.z, o.x, d.x, o.y, d.y, ia, ib, t_lo, t_hi, t_out);
 }
+#endif
 
 // rect_prism (object.rs:420-473) as ONE record {p0, p1}: the six Rect::hit calls of its And tree (object.rs:396-410),
 // in the tree's visiting order — z = p1.z, y = p1.y, x = p1.x, then the FlipNormals faces z = p0.z, y = p0.y,

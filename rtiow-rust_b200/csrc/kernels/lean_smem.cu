@@ -1,4 +1,5 @@
 // The "lean general" megakernel (kFeatLean): its own translation unit so that it compiles in parallel with the others.
+#define RT_RECT_OUTLINE 1  // path_logic.cuh: this kernel is bound by instruction fetch
 #include "../abi/kernel_table.hpp"
 #include "../device/render_kernel.cuh"
 
