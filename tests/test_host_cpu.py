@@ -258,6 +258,43 @@ def test_prism_fusion_and_general_medium_boundaries_match_the_oracle(oracle):
                 assert int(smp[..., 3].sum()) == cnt["segments"], (name, bvh, accel, fuse)
 
 
+def test_prism_items_supplied_by_the_host(oracle):
+    """RTIOW_ITEM_PRISM is also part of the ABI: a host may send `rect_prism(p0, p1, m)` (object.rs:420-473) as one item
+    instead of the six Rect items of its And tree.  The Cornell box with its two prisms rewritten that way by hand renders
+    the oracle's bits, in every traversal mode."""
+    nx, ny, ns = 40, 40, 5
+    world, cam = R.build_scene("cornell", nx, ny, use_bvh=False)
+    d = world.desc.contents
+    src = (N.Item * d.n_items)()
+    C.memmove(src, d.items, C.sizeof(src))
+    out, i = [], 0
+    while i < d.n_items:
+        run = [src[i + k] for k in range(6)] if i + 6 <= d.n_items else []
+        axes = [((it.b_w >> 24) >> 2) & 3 for it in run]
+        if run and all((it.a_w & 15) == 3 for it in run) and axes == [2, 1, 0, 2, 1, 0] and len({it.a_w >> 4 for it in run}) == 1:
+            p = N.Item()                                    # a = p0, b = p1 (see include/rtiow_b200.h)
+            p.a[0], p.a[1], p.a[2] = run[5].a[0], run[4].a[0], run[3].a[0]      # k of the x, y, z faces at p0
+            p.b[0], p.b[1], p.b[2] = run[2].a[0], run[1].a[0], run[0].a[0]      # k of the x, y, z faces at p1
+            p.a_w = 6 | (run[0].a_w & ~15)
+            p.b_w = run[0].b_w & 0x00FFFFFF
+            out.append(p)
+            i += 6
+        else:
+            out.append(src[i])
+            i += 1
+    assert len(out) == d.n_items - 10                       # two prisms
+    items = (N.Item * len(out))(*out)
+    desc = _desc_copy(world)
+    desc.items = items
+    desc.n_items = len(out)
+    assert N.abi().rtiow_b200_scene_validate(C.byref(desc)) == 0, N.abi().rtiow_b200_last_error()
+    want, _, _ = oracle.Scene("cornell", nx, ny, top_level_bvh=False).render(ns, nthreads=4)
+    for accel in (1, 2, 0):
+        img = np.zeros((ny, nx, 3), np.float32)
+        rc = H.lib().harness_render(C.byref(desc), C.byref(cam.rec), nx, ny, ns, 0xDEADBEEF, 0, ny, img.ctypes.data, None, accel, None, 1, 1)
+        assert rc == 0 and n_diff(img, want) == 0, accel
+
+
 def test_medium_boundary_validation():
     world, _ = R.build_scene("cornell_smoke", 16, 16, use_bvh=False)
     lib = N.abi()
