@@ -242,8 +242,9 @@ RTIOW_API int rtiow_b200_render_rows_strided_device(rtiow_scene_t* scene, const 
 
 /* ---------------------------------------------------------------------------------------------
  * Several GPUs.  par_cast parallelises over scanlines (src/lib.rs:324-332); here the frame is cut into
- * bands of `band_rows` scanlines dealt round-robin to the GPUs (GPU g: bands g, g + G, ...), every GPU
- * renders its bands with its own copy of the scene, and the kernel that finishes a pixel (the
+ * bands of `band_rows` scanlines dealt to the GPUs in serpentine order (GPU g: band g of the first G bands,
+ * band G-1-g of the next G, ...: cost grows from the sky at the top of a frame to the ground at its bottom, and the
+ * serpentine cancels that gradient between the GPUs), every GPU renders its bands with its own copy of the scene, and the kernel that finishes a pixel (the
  * in-order sample fold) stores it straight into the frame of every GPU that wants it, through NVLink
  * peer pointers, at the row's final position: the framebuffer exchange is fused into the fold, there is
  * no all-gather and no de-interleave pass behind it.  Every row is bit-identical to the same row of
@@ -259,7 +260,8 @@ RTIOW_API int rtiow_b200_render_multi(rtiow_scene_t* const* scenes, int ngpus, c
 
 typedef struct rtiow_peer_frame rtiow_peer_frame_t;
 #define RTIOW_PEER_HANDLE_BYTES 128u
-/* This rank's copy of the ny*nx*3 float frame (+ hand-shake flags) on `device`; n_ranks <= 16. */
+/* This rank's copy of the ny*nx*3 float frame on `device` — two buffers, consecutive renders alternate between
+ * them — plus the hand-shake flags; n_ranks <= 16. */
 RTIOW_API int rtiow_b200_peer_frame_create(int device, uint32_t nx, uint32_t ny, uint32_t rank, uint32_t n_ranks,
                                            rtiow_peer_frame_t** out);
 /* RTIOW_PEER_HANDLE_BYTES bytes that let another rank (another process, or this one) map this frame. */
@@ -267,14 +269,18 @@ RTIOW_API int rtiow_b200_peer_frame_export(rtiow_peer_frame_t* frame, uint8_t* h
 /* `handles`: the exported handles of all n_ranks ranks, in rank order.  Maps the peers' frames (CUDA IPC across
  * processes, peer access inside one). */
 RTIOW_API int rtiow_b200_peer_frame_connect(rtiow_peer_frame_t* frame, const uint8_t* handles);
-/* DEVICE pointer to this rank's frame: ny*nx*3 floats, row 0 = top. */
+/* DEVICE pointer to the frame the most recent rtiow_b200_render_rows_peers call on `frame` assembles: ny*nx*3 floats,
+ * row 0 = top.  Ask again after every render (the two buffers alternate); the pointer stays valid, and its contents
+ * stay untouched, until the end of the NEXT render on this frame. */
 RTIOW_API int rtiow_b200_peer_frame_ptr(rtiow_peer_frame_t* frame, float** d_frame);
 RTIOW_API void rtiow_b200_peer_frame_destroy(rtiow_peer_frame_t* frame);
-/* This rank's share of par_cast, enqueued on `cuda_stream`: signals "my frame may be overwritten", renders bands
- * rank, rank + n_ranks, ... , waits for every peer's signal, folds the samples into EVERY rank's frame, signals
- * "my rows are there" and waits for everybody's.  When the stream reaches the end the frame of this rank holds the
- * whole image.  All ranks must make the same sequence of calls; a rank that does not arrive within 60 s makes the
- * next call fail instead of hanging the GPU. */
+/* This rank's share of par_cast, enqueued on `cuda_stream`: renders this rank's bands, folds the samples into EVERY
+ * rank's frame, then one barrier: signals "my rows are there" and waits for everybody's.  When the stream reaches the
+ * end the frame of this rank (rtiow_b200_peer_frame_ptr) holds the whole image.  Nothing waits before the fold: it
+ * writes the buffer the ranks read two renders ago, and every rank enters a barrier only after the reads it enqueued
+ * before that call — so whatever reads a frame must be enqueued on the stream of the next call, before it.  All ranks
+ * must make the same sequence of calls; a rank that does not arrive within 60 s makes the next call fail instead of
+ * hanging the GPU. */
 RTIOW_API int rtiow_b200_render_rows_peers(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny,
                                            uint32_t ns, uint64_t seed, uint32_t band_rows, rtiow_peer_frame_t* frame,
                                            void* cuda_stream);

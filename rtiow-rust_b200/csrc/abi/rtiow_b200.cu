@@ -325,6 +325,7 @@ struct rtiow_scene {
 
     // tuning
     uint32_t cta_threads = 0, ctas_per_sm = 0, staging_mib = 0, sample_chunk = 0;
+    bool serpentine = true;        // RTIOW_B200_SERPENTINE=0: plain round-robin bands in multi-GPU renders
     bool force_global = false;
     uint32_t features = 0;         // scene_blob.hpp scene_features()
     bool specialise = true;        // use a kernel compiled for a subset of features when the scene allows (same image)
@@ -387,14 +388,10 @@ int check_render_args(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, ui
     return RTIOW_OK;
 }
 
-// Where a multi-GPU render puts its rows and how it meets its peers (rtiow_b200_render_rows_peers).
+// Where a multi-GPU render puts its rows (rtiow_b200_render_rows_peers).
 struct PeerTarget {
-    rtiow::FoldDst dst{};          // every rank's frame, rows at their position in the image
-    rtiow::PeerFlags ready{};      // slot [rank] of every rank's "ready" array
-    const unsigned int* my_ready = nullptr;
-    unsigned int epoch = 0;
-    uint32_t n_ranks = 1;
-    unsigned int* timed_out = nullptr;
+    rtiow::FoldDst dst{};          // every rank's frame (the buffer of this epoch), rows at their position in the image
+    uint32_t row_begin_odd = 0;    // first row of this rank's band in the odd periods (serpentine deal)
 };
 constexpr unsigned long long kPeerTimeoutNs = 60ull * 1000ull * 1000ull * 1000ull;
 
@@ -404,9 +401,15 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
                    uint32_t r0, uint32_t r1, float* d_out, float4* d_samples, cudaStream_t stream, uint32_t step = 1,
                    uint32_t band = 1, const PeerTarget* peers = nullptr) {
     CK(cudaSetDevice(s->device));
-    // bands of `band` rows starting at r0, r0 + step, ..., clipped to r1
-    const uint32_t n_full = (r1 - r0) / step, rest = (r1 - r0) - n_full * step;
-    const uint32_t n_rows = n_full * band + std::min(rest, band);
+    // bands of `band` rows starting at r0, r0 + step, ..., clipped to r1; with peers (serpentine deal, KParams) the odd
+    // bands start at r0_odd + step, r0_odd + 3 step, ...
+    const uint32_t r0_odd = peers ? peers->row_begin_odd : r0;
+    uint32_t n_rows = 0;
+    for (uint64_t b = 0;; ++b) {
+        const uint64_t begin = ((b & 1u) ? r0_odd : r0) + b * step;
+        if (begin >= r1) break;
+        n_rows += static_cast<uint32_t>(std::min<uint64_t>(band, r1 - begin));
+    }
     const uint64_t npix64 = static_cast<uint64_t>(n_rows) * nx;
     const uint32_t npix = static_cast<uint32_t>(npix64);
     Workspace& W = *s->ws;
@@ -497,7 +500,7 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     P.off_tex = B.lay.off_tex; P.off_pvecs = B.lay.off_pvecs; P.off_pperm = B.lay.off_pperm;
     P.off_fnodes = B.lay.off_fnodes;
     std::memcpy(P.cam, cam, sizeof(float) * 21);
-    P.nx = nx; P.ny = ny; P.row_begin = r0; P.n_rows = n_rows; P.row_step = step; P.row_band = band;
+    P.nx = nx; P.ny = ny; P.row_begin = r0; P.row_begin_odd = r0_odd; P.n_rows = n_rows; P.row_step = step; P.row_band = band;
     P.npix = npix; P.tiles_x = tiles_x;
     P.key0 = static_cast<uint32_t>(seed); P.key1 = static_cast<uint32_t>(seed >> 32);
     P.bg_kind = s->bg_kind;
@@ -535,11 +538,15 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
             K.s_chunk = std::min(s->sample_chunk, s_count);
             K.s_tail_begin = s_count;
         } else if (s->bg_kind == RTIOW_BG_SKY_GRADIENT) {
-            // open scenes (most units are cheap sky): ONE size, the largest of 8, 4, 2, 1 that leaves every resident warp ~48
-            // units — measured on book-1: 10.68 ms against 10.97 ms with a tail of smaller units; closed scenes (Cornell:
-            // every path is long) gain 3 % from the tail instead
+            // open scenes (most units are cheap sky): ONE size — measured on book-1: 10.68 ms against 10.97 ms with a tail
+            // of smaller units; closed scenes (Cornell: every path is long) gain 3 % from the tail instead.  Which size: a
+            // larger unit saves a share of the whole render (coherent camera rays, fewer atomics), its tail costs a fixed
+            // time, so the best size grows with the square root of the work per warp: the largest c of 8, 4, 2, 1 with
+            // 4 c^2 <= (one-sample units per resident warp) hits the measured optimum for the full book-1 frame and for a
+            // half, a quarter and an eighth of it (profiles/r02/p1_unit_size/)
+            const uint64_t units1 = static_cast<uint64_t>(n_groups) * s_count;
             uint32_t c = 8u;
-            while (c > 1u && static_cast<uint64_t>(n_groups) * ((s_count + c - 1) / c) < 48ull * resident_warps) c >>= 1;
+            while (c > 1u && 4ull * c * c * resident_warps > units1) c >>= 1;
             K.s_chunk = std::min(c, s_count);
             K.s_tail_begin = s_count;
         } else {
@@ -609,16 +616,8 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
             rtiow::FoldDst dst{};
             if (peers) {
                 dst = peers->dst;
-                dst.nx = nx; dst.row_begin = r0; dst.row_step = step; dst.row_band = band;
+                dst.nx = nx; dst.row_begin = r0; dst.row_begin_odd = r0_odd; dst.row_step = step; dst.row_band = band;
                 dst.image_rows = 1u;
-                if (pass + 1 == n_pass && peers->n_ranks > 1) {
-                    // the last fold writes into the peers' frames: not before every peer has finished with the previous
-                    // frame (its "ready" for this epoch was enqueued at the start of its call, long ago by now)
-                    rtiow::peer_wait_kernel<<<1, 32, 0, stream>>>(peers->my_ready, peers->n_ranks, peers->epoch, kPeerTimeoutNs,
-                                                                  peers->timed_out);
-                    CK(cudaGetLastError());
-                    ++launches;
-                }
             } else {
                 dst.p[0] = d_out;
                 dst.n = 1u;
@@ -729,6 +728,7 @@ int rtiow_b200_scene_create(const rtiow_scene_desc_t* d, int device, rtiow_scene
     if (const char* env = std::getenv("RTIOW_B200_UNIT_ORDER")) s->bottom_first = std::atoi(env) != 0;
     if (const char* env = std::getenv("RTIOW_B200_PHASE_SYNC")) s->phase_sync = std::max(0, std::atoi(env));
     if (const char* env = std::getenv("RTIOW_B200_PHASE_GROUP")) s->phase_group_env = static_cast<uint32_t>(std::max(1, std::atoi(env)));
+    if (const char* env = std::getenv("RTIOW_B200_SERPENTINE")) s->serpentine = std::atoi(env) != 0;
     if (const char* env = std::getenv("RTIOW_B200_SAMPLE_CHUNK")) s->sample_chunk = static_cast<uint32_t>(std::max(0, std::atoi(env)));
     {   // build + upload the blob of the selected traversal now, so that render calls only launch
         const rtiow::BlobMode mode = s->traversal == RTIOW_TRAVERSAL_REFERENCE_ORDER ? rtiow::kBlobReferenceOrder
@@ -877,8 +877,9 @@ int rtiow_b200_render_ppm(rtiow_scene_t* s, const rtiow_camera_t* cam, uint32_t 
 
 }  // extern "C"
 
-// One rank's copy of the frame plus its hand-shake flags, in ONE cudaMalloc allocation that the other ranks map
-// (CUDA IPC between processes, peer access inside one): [frame ny*nx*3 f32 | ready[16] u32 | done[16] u32].
+// One rank's two copies of the frame (epoch e is assembled in buffer e & 1, aux_kernels.cuh) plus its hand-shake flags, in
+// ONE cudaMalloc allocation that the other ranks map (CUDA IPC between processes, peer access inside one):
+// [frame 0: ny*nx*3 f32 | frame 1 | arrived[16] u32].
 struct rtiow_peer_frame {
     int device = 0;
     uint32_t nx = 0, ny = 0, rank = 0, n_ranks = 1;
@@ -888,12 +889,11 @@ struct rtiow_peer_frame {
     bool opened_ipc[rtiow::kMaxFoldDst] = {};
     bool connected = false;
     unsigned int epoch = 0;
-    unsigned int* timed_out = nullptr;         // pinned, mapped: the wait kernels raise it, the host reads it without a sync
+    unsigned int* timed_out = nullptr;         // pinned, mapped: the barrier kernel raises it, the host reads it without a sync
     cudaEvent_t done_ev = nullptr;             // single-process multi-GPU: end of this device's part
 
-    float* frame(uint32_t q) const { return reinterpret_cast<float*>(peer_base[q]); }
-    unsigned int* ready(uint32_t q) const { return reinterpret_cast<unsigned int*>(peer_base[q] + frame_bytes); }
-    unsigned int* done(uint32_t q) const { return ready(q) + rtiow::kMaxFoldDst; }
+    float* frame(uint32_t q, unsigned int e) const { return reinterpret_cast<float*>(peer_base[q] + (e & 1u) * frame_bytes); }
+    unsigned int* arrived(uint32_t q) const { return reinterpret_cast<unsigned int*>(peer_base[q] + 2u * frame_bytes); }
 };
 
 namespace {
@@ -913,7 +913,7 @@ constexpr uint32_t kPeerMagic = 0x52543230u;
 uint64_t my_pid();
 
 // Renders rank `pf->rank`'s bands of `band` rows into the frames listed in `dst_ranks` (a bit mask) and, if `handshake`,
-// runs the ready / done protocol with all ranks.
+// ends with the barrier that makes the frame whole on every rank.
 int render_bands(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny, uint32_t ns, uint64_t seed, uint32_t band,
                  rtiow_peer_frame* pf, uint32_t dst_mask, bool handshake, cudaStream_t stream) {
     if (!pf->connected && pf->n_ranks > 1) return set_err(RTIOW_ERR_INVALID_ARG, "peer frame is not connected");
@@ -921,36 +921,25 @@ int render_bands(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint32_
     if (s->device != pf->device) return set_err(RTIOW_ERR_INVALID_ARG, "scene and peer frame live on different devices");
     if (*pf->timed_out) return set_err(RTIOW_ERR_CUDA, "a peer did not arrive within the time-out in an earlier multi-GPU render");
     CK(cudaSetDevice(s->device));
+    // bands are dealt in serpentine order: ranks 0..G-1 in even periods of G bands, G-1..0 in odd ones — in the reference's
+    // scenes cost grows from the top of the frame (sky, one segment) to the bottom, and with a plain round-robin the last
+    // rank's rows are all 4 (G-1) rows further down than the first's: 1.6-2.7 % more work on 8 GPUs (profiles/r02)
     const uint32_t G = pf->n_ranks, r0 = pf->rank * band, step = G * band;
     PeerTarget T{};
-    T.n_ranks = G;
-    T.epoch = ++pf->epoch;
-    T.timed_out = pf->timed_out;
-    T.my_ready = pf->ready(pf->rank);
-    rtiow::PeerFlags done{};
+    T.row_begin_odd = s->serpentine ? (G - 1u - pf->rank) * band : r0;
+    const unsigned int epoch = ++pf->epoch;
+    rtiow::PeerFlags arrived{};
     for (uint32_t q = 0; q < G; ++q) {
-        if (dst_mask & (1u << q)) T.dst.p[T.dst.n++] = pf->frame(q);
-        T.ready.p[q] = pf->ready(q);
-        done.p[q] = pf->done(q);
+        if (dst_mask & (1u << q)) T.dst.p[T.dst.n++] = pf->frame(q, epoch);
+        arrived.p[q] = pf->arrived(q);
     }
-    T.ready.n = done.n = G;
-    const bool sync = handshake && G > 1;
-    if (sync) {  // "I am done with the previous frame": peers may overwrite my copy from their next fold on
-        rtiow::peer_signal_kernel<<<1, 32, 0, stream>>>(T.ready, pf->rank, T.epoch);
-        CK(cudaGetLastError());
-    }
-    PeerTarget Tq = T;
-    if (!sync) Tq.n_ranks = 1;  // no wait before the fold
-    if (r0 < ny) {
-        if (int rc = enqueue_render(s, cam, nx, ny, ns, seed, r0, ny, nullptr, nullptr, stream, step, band, &Tq)) return rc;
-    } else if (sync) {  // more ranks than bands: nothing to render, but the protocol still runs
-        rtiow::peer_wait_kernel<<<1, 32, 0, stream>>>(T.my_ready, G, T.epoch, kPeerTimeoutNs, T.timed_out);
-        CK(cudaGetLastError());
-    }
-    if (sync) {  // my rows are in every frame -> tell everybody; the frame is whole once everybody has told me
-        rtiow::peer_signal_kernel<<<1, 32, 0, stream>>>(done, pf->rank, T.epoch);
-        CK(cudaGetLastError());
-        rtiow::peer_wait_kernel<<<1, 32, 0, stream>>>(pf->done(pf->rank), G, T.epoch, kPeerTimeoutNs, T.timed_out);
+    arrived.n = G;
+    // No wait before the fold: it overwrites the peers' copies of frame epoch - 2, and this stream is already past the
+    // barrier of epoch - 1, which every peer entered after its reads of that frame (aux_kernels.cuh).
+    if (r0 < ny)  // (more ranks than bands: nothing to render, but the barrier still runs)
+        if (int rc = enqueue_render(s, cam, nx, ny, ns, seed, r0, ny, nullptr, nullptr, stream, step, band, &T)) return rc;
+    if (handshake && G > 1) {  // my rows are in every frame -> tell everybody; the frame is whole once everybody has told me
+        rtiow::peer_barrier_kernel<<<1, 32, 0, stream>>>(arrived, pf->rank, epoch, kPeerTimeoutNs, pf->timed_out);
         CK(cudaGetLastError());
         CK(s->ws->mark_render_end(stream));
     }
@@ -973,7 +962,7 @@ int rtiow_b200_peer_frame_create(int device, uint32_t nx, uint32_t ny, uint32_t 
     auto pf = new rtiow_peer_frame();
     pf->device = device; pf->nx = nx; pf->ny = ny; pf->rank = rank; pf->n_ranks = n_ranks;
     pf->frame_bytes = (static_cast<size_t>(nx) * ny * 3 * sizeof(float) + 255u) / 256u * 256u;
-    pf->bytes = pf->frame_bytes + 2u * rtiow::kMaxFoldDst * sizeof(unsigned int);
+    pf->bytes = 2u * pf->frame_bytes + rtiow::kMaxFoldDst * sizeof(unsigned int);
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&pf->base), pf->bytes);  // plain cudaMalloc: exportable with CUDA IPC
     if (e == cudaSuccess) e = cudaMemset(pf->base, 0, pf->bytes);
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&pf->timed_out), sizeof(unsigned int), cudaHostAllocMapped);
@@ -1041,7 +1030,7 @@ int rtiow_b200_peer_frame_connect(rtiow_peer_frame_t* pf, const uint8_t* handles
 
 int rtiow_b200_peer_frame_ptr(rtiow_peer_frame_t* pf, float** d_frame) {
     if (!pf || !d_frame) return set_err(RTIOW_ERR_INVALID_ARG, "null argument");
-    *d_frame = pf->frame(pf->rank);
+    *d_frame = pf->frame(pf->rank, pf->epoch);
     return RTIOW_OK;
 }
 
@@ -1131,7 +1120,7 @@ int rtiow_b200_render_multi(rtiow_scene_t* const* scenes, int ngpus, const rtiow
         Workspace& W0 = *scenes[0]->ws;
         cudaError_t e = cudaSetDevice(scenes[0]->device);
         for (uint32_t g = 1; g < G && e == cudaSuccess; ++g) e = cudaStreamWaitEvent(W0.stream, pf[g]->done_ev, 0);
-        if (e == cudaSuccess) e = W0.copy_to_host(out_rgb, pf[0]->frame(0), static_cast<size_t>(nx) * ny * 3 * sizeof(float));
+        if (e == cudaSuccess) e = W0.copy_to_host(out_rgb, pf[0]->frame(0, pf[0]->epoch), static_cast<size_t>(nx) * ny * 3 * sizeof(float));
         if (e != cudaSuccess) rc = set_err(RTIOW_ERR_CUDA, std::string("render_multi gather: ") + cudaGetErrorString(e));
     }
     return rc;

@@ -13,14 +13,15 @@ namespace rtiow {
 // Where the finished pixel goes: to `n` frames (this GPU's and, through NVLink peer pointers, the
 // other GPUs': the fold IS the framebuffer exchange, there is no all-gather behind it), either packed
 // (pixel p of the rendered row block -> p) or at the row's position in the whole image (packed row r
-// = image row row_begin + (r / row_band) * row_step + r % row_band).
+// = row r % row_band of band b = r / row_band, which starts at image row (b odd ? row_begin_odd : row_begin) + b * row_step;
+// KParams in path_logic.cuh).
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxFoldDst = 16;
 struct FoldDst {
     float* p[kMaxFoldDst];
     uint32_t n;
     uint32_t image_rows;  // 0: packed; 1: rows land at their position in the ny x nx image
-    uint32_t nx, row_begin, row_step, row_band;
+    uint32_t nx, row_begin, row_begin_odd, row_step, row_band;
 };
 
 __global__ void __launch_bounds__(256) fold_kernel(const float4* __restrict__ staging, float4* __restrict__ accum,
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(256) fold_kernel(const float4* __restrict__ st
             if (dst.image_rows) {
                 const uint32_t r = p / dst.nx, x = p - r * dst.nx;
                 const uint32_t band = r / dst.row_band;
-                const uint32_t row = dst.row_begin + band * dst.row_step + (r - band * dst.row_band);
+                const uint32_t row = ((band & 1u) ? dst.row_begin_odd : dst.row_begin) + band * dst.row_step + (r - band * dst.row_band);
                 o = 3u * (static_cast<size_t>(row) * dst.nx + x);
             }
             const float cr = acc.x / ns_f, cg = acc.y / ns_f, cb = acc.z / ns_f;
@@ -64,35 +65,33 @@ __global__ void __launch_bounds__(256) fold_kernel(const float4* __restrict__ st
 }
 
 // ------------------------------------------------------------------------------------------------
-// Cross-GPU hand-shake of the peer-store exchange (rtiow_b200_render_rows_peers).  Every rank owns
-// two flag arrays in its peer-visible allocation: flags[q] is written by rank q only.
-//   signal: after everything enqueued before it on the stream, publish `epoch` into MY slot of every
-//           rank's array (system-scope release);
-//   wait:   spin (system-scope acquire) until every slot of MY array has reached `epoch`, with a
+// Cross-GPU hand-shake of the peer-store exchange (rtiow_b200_render_rows_peers): ONE barrier per frame.
+// Every rank owns a flag array in its peer-visible allocation; flags[q] is written by rank q only.
+//   arrive: after everything enqueued before this kernel on the stream (the fold that stored my rows into every rank's
+//           frame), publish `epoch` into MY slot of every rank's array (system-scope release);
+//   wait:   spin (system-scope acquire) until every slot of MY array has reached `epoch` — the frame is whole — with a
 //           time-out so that a rank that never arrives cannot hang the GPU: *timed_out is set instead.
+// One barrier is enough because the frames are double-buffered (rtiow_peer_frame): epoch e is assembled in buffer
+// e & 1, so a fold of epoch e + 2 overwrites what its peers read as frame e — and a peer publishes epoch e + 1 only after
+// what it enqueued before that call, its reads of frame e included.
 // ------------------------------------------------------------------------------------------------
 struct PeerFlags {
     unsigned int* p[kMaxFoldDst];  // rank q's flag array (peer pointer)
     uint32_t n;
 };
 
-__global__ void peer_signal_kernel(const __grid_constant__ PeerFlags flags, uint32_t my_rank, unsigned int epoch) {
+__global__ void peer_barrier_kernel(const __grid_constant__ PeerFlags flags, uint32_t my_rank, unsigned int epoch,
+                                    unsigned long long timeout_ns, unsigned int* __restrict__ timed_out) {
     const uint32_t q = threadIdx.x;
     __threadfence_system();  // the frame stores of the kernels before this one, cumulatively
-    if (q < flags.n) {
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags.p[q] + my_rank), "r"(epoch) : "memory");
-    }
-}
-
-__global__ void peer_wait_kernel(const unsigned int* __restrict__ my_flags, uint32_t n, unsigned int epoch,
-                                 unsigned long long timeout_ns, unsigned int* __restrict__ timed_out) {
-    const uint32_t q = threadIdx.x;
-    if (q >= n) return;
+    if (q >= flags.n) return;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags.p[q] + my_rank), "r"(epoch) : "memory");
+    const unsigned int* mine = flags.p[my_rank] + q;
     unsigned long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (;;) {
         unsigned int v;
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(my_flags + q) : "memory");
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
         if (static_cast<int>(v - epoch) >= 0) break;
         unsigned long long t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
@@ -100,7 +99,7 @@ __global__ void peer_wait_kernel(const unsigned int* __restrict__ my_flags, uint
             atomicExch(timed_out, 1u);
             break;
         }
-        __nanosleep(200);
+        __nanosleep(100);
     }
 }
 

@@ -125,9 +125,17 @@ class PeerFrame:
         import torch
         blob = (C.c_uint8 * (N.PEER_HANDLE_BYTES * self.world_size)).from_buffer_copy(b"".join(handles))
         api._check(self.lib.rtiow_b200_peer_frame_connect(self.h, blob), self.lib)
+        self._views = {}
+        self._latest()
+
+    def _latest(self):
+        """`frame` = the buffer the most recent render assembled (the library alternates between two, one per epoch)."""
+        import torch
         ptr = C.c_void_p()
         api._check(self.lib.rtiow_b200_peer_frame_ptr(self.h, C.byref(ptr)), self.lib)
-        self.frame = torch.as_tensor(_DeviceArray(ptr.value, (self.ny, self.nx, 3)), device=f"cuda:{self.device_index}")
+        if ptr.value not in self._views:
+            self._views[ptr.value] = torch.as_tensor(_DeviceArray(ptr.value, (self.ny, self.nx, 3)), device=f"cuda:{self.device_index}")
+        self.frame = self._views[ptr.value]
 
     def render(self, nx, ny, ns, camera, world, band_rows, seed=api.DEFAULT_SEED, stream=None):
         """This rank's share (rtiow_b200_render_rows_peers), enqueued on `stream` (default: current)."""
@@ -135,17 +143,19 @@ class PeerFrame:
         s = stream if stream is not None else torch.cuda.current_stream(self.device_index)
         api._check(self.lib.rtiow_b200_render_rows_peers(world.gpu(self.device_index), C.byref(camera.rec), nx, ny, ns, seed, band_rows,
                                                          self.h, C.c_void_p(s.cuda_stream)), self.lib)
+        self._latest()
 
     def close(self):
         if self.h:
             self.frame = None
+            self._views = {}
             self.lib.rtiow_b200_peer_frame_destroy(self.h)
             self.h = None
 
 
 class ShardBuffers:
-    """Device buffers of one rank, allocated once.  Peer exchange: `frame` is this rank's peer-visible frame, every rank's
-    fold writes into it.  NCCL exchange: `mine` (this rank's packed rows, padded to max_rows), `parts` (everybody's),
+    """Device buffers of one rank, allocated once.  Peer exchange: `frame` is this rank's peer-visible frame of the latest
+    render (two buffers alternate), every rank's fold writes into it.  NCCL exchange: `mine` (this rank's packed rows, padded to max_rows), `parts` (everybody's),
     `frame` (the assembled image)."""
 
     def __init__(self, nx, ny, shard, device, world=None, exchange="auto"):
@@ -168,12 +178,12 @@ class ShardBuffers:
                 self.peer.close()
                 self.peer = None
         if self.peer is not None:
-            self.frame = self.peer.frame
+            self._frame = None
             self.mine = self.parts = None
             self.exchange = ("fused into the sample fold: every finished row is stored into every rank's frame through NVLink peer "
                              "pointers (rtiow_b200_render_rows_peers); no collective on the data path")
             return
-        self.frame = torch.empty((ny, nx, 3), dtype=torch.float32, device=device)
+        self._frame = torch.empty((ny, nx, 3), dtype=torch.float32, device=device)
         self.exchange = "none (one rank)" if shard.world_size == 1 else "one NCCL all_gather_into_tensor of the packed rows" + (
             " + one strided de-interleave copy" if (shard.interleaved or not shard.uniform) else ", in place")
         if shard.world_size == 1:
@@ -186,9 +196,12 @@ class ShardBuffers:
             self.parts = None
             self.mine = self.frame[shard.begin:shard.end]
 
+    @property
+    def frame(self):
+        return self.peer.frame if self.peer is not None else self._frame
 
     def close(self):
-        self.frame = self.mine = self.parts = None
+        self._frame = self.mine = self.parts = None
         if self.peer is not None:
             self.peer.close()
             self.peer = None

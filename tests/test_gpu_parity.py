@@ -313,9 +313,8 @@ def test_band_shards_of_every_world_size_assemble_to_the_same_bits(G):
 
 def test_peer_store_exchange_two_ranks_on_one_gpu():
     """The multi-GPU exchange (rtiow_b200_render_rows_peers: the fold stores every finished row into every rank's frame,
-    then the ready / done hand-shake) with both ranks on this one GPU: two scene handles, two streams, two peer frames
-    mapped into each other.  Both frames must hold the whole image, bit-identical to the single-launch frame, call
-    after call (the hand-shake also guards the frames against the next call's stores)."""
+    then one barrier) with both ranks on this one GPU: two scene handles, two streams, two peer frames mapped into each
+    other.  Both frames must hold the whole image, bit-identical to the single-launch frame, call after call."""
     import torch
     from rtiow_rust_b200 import dist as rdist
     nx, ny, ns, G = 200, 150, 6, 2
@@ -335,6 +334,22 @@ def test_peer_store_exchange_two_ranks_on_one_gpu():
             st.synchronize()
         for r in range(G):
             assert bits_equal(frames[r].frame.cpu().numpy(), want), (seed, r)
+    # the same without the host in between: six renders queued back to back, each frame copied out on its rank's stream
+    # right behind its render — the two buffers of a peer frame alternate, and only the barrier of render e + 1 keeps the
+    # fold of render e + 2 off the buffer that copy reads
+    seeds = [11, 12, 13, 14, 15, 16]
+    snaps = [[None] * len(seeds) for _ in range(G)]
+    for i, seed in enumerate(seeds):
+        for r in range(G):
+            frames[r].render(nx, ny, ns, cam, worlds[r][0], band, seed=seed, stream=streams[r])
+            with torch.cuda.stream(streams[r]):
+                snaps[r][i] = frames[r].frame.clone()
+    for st in streams:
+        st.synchronize()
+    for i, seed in enumerate(seeds):
+        want = R.par_cast(nx, ny, ns, cam, worlds[0][0], seed=seed).rgb
+        for r in range(G):
+            assert bits_equal(snaps[r][i].cpu().numpy(), want), (seed, r)
     for f in frames:
         f.close()
 
