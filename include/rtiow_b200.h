@@ -241,19 +241,18 @@ RTIOW_API int rtiow_b200_render_rows_strided_device(rtiow_scene_t* scene, const 
                                           uint32_t row_step, uint32_t band_rows, float* d_out_rows, void* cuda_stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Several GPUs.  par_cast parallelises over scanlines (src/lib.rs:324-332); here the frame is cut into
- * bands of `band_rows` scanlines dealt to the GPUs in serpentine order (GPU g: band g of the first G bands,
- * band G-1-g of the next G, ...: cost grows from the sky at the top of a frame to the ground at its bottom, and the
- * serpentine cancels that gradient between the GPUs), every GPU renders its bands with its own copy of the scene, and the kernel that finishes a pixel (the
- * in-order sample fold) stores it straight into the frame of every GPU that wants it, through NVLink
- * peer pointers, at the row's final position: the framebuffer exchange is fused into the fold, there is
- * no all-gather and no de-interleave pass behind it.  Every row is bit-identical to the same row of
- * rtiow_b200_render, for any number of GPUs.
+ * Several GPUs.  par_cast parallelises over scanlines (src/lib.rs:324-332); here the frame's 8x4-pixel tiles are
+ * dealt round-robin to the GPUs (GPU g: tiles g, g + G, ... in row-major tile order, so every GPU's share is spread
+ * evenly over the image: shares of whole scanline bands differed by 6 % in work on book-1, tiles by well under 1 %),
+ * every GPU renders its tiles with its own copy of the scene, and the kernel that finishes a pixel (the in-order
+ * sample fold) stores it straight into the frame of every GPU that wants it, through NVLink peer pointers, at its
+ * final position: the framebuffer exchange is fused into the fold, there is no all-gather and no de-interleave pass
+ * behind it.  Every pixel is bit-identical to the same pixel of rtiow_b200_render, for any number of GPUs.
  *
  * One host process: rtiow_b200_render_multi is par_cast over `ngpus` scene handles (one per device,
  * created from the same descriptor).  One process per GPU (torchrun, MPI): each rank creates a peer
  * frame, the opaque handles are exchanged by whatever transport the host has, and
- * rtiow_b200_render_rows_peers leaves the whole image in every rank's frame.
+ * rtiow_b200_render_peers leaves the whole image in every rank's frame.
  * ------------------------------------------------------------------------------------------- */
 RTIOW_API int rtiow_b200_render_multi(rtiow_scene_t* const* scenes, int ngpus, const rtiow_camera_t* camera, uint32_t nx,
                                       uint32_t ny, uint32_t ns, uint64_t seed, float* out_rgb);
@@ -269,21 +268,20 @@ RTIOW_API int rtiow_b200_peer_frame_export(rtiow_peer_frame_t* frame, uint8_t* h
 /* `handles`: the exported handles of all n_ranks ranks, in rank order.  Maps the peers' frames (CUDA IPC across
  * processes, peer access inside one). */
 RTIOW_API int rtiow_b200_peer_frame_connect(rtiow_peer_frame_t* frame, const uint8_t* handles);
-/* DEVICE pointer to the frame the most recent rtiow_b200_render_rows_peers call on `frame` assembles: ny*nx*3 floats,
+/* DEVICE pointer to the frame the most recent rtiow_b200_render_peers call on `frame` assembles: ny*nx*3 floats,
  * row 0 = top.  Ask again after every render (the two buffers alternate); the pointer stays valid, and its contents
  * stay untouched, until the end of the NEXT render on this frame. */
 RTIOW_API int rtiow_b200_peer_frame_ptr(rtiow_peer_frame_t* frame, float** d_frame);
 RTIOW_API void rtiow_b200_peer_frame_destroy(rtiow_peer_frame_t* frame);
-/* This rank's share of par_cast, enqueued on `cuda_stream`: renders this rank's bands, folds the samples into EVERY
+/* This rank's share of par_cast, enqueued on `cuda_stream`: renders this rank's tiles, folds the samples into EVERY
  * rank's frame, then one barrier: signals "my rows are there" and waits for everybody's.  When the stream reaches the
  * end the frame of this rank (rtiow_b200_peer_frame_ptr) holds the whole image.  Nothing waits before the fold: it
  * writes the buffer the ranks read two renders ago, and every rank enters a barrier only after the reads it enqueued
  * before that call — so whatever reads a frame must be enqueued on the stream of the next call, before it.  All ranks
  * must make the same sequence of calls; a rank that does not arrive within 60 s makes the next call fail instead of
  * hanging the GPU. */
-RTIOW_API int rtiow_b200_render_rows_peers(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny,
-                                           uint32_t ns, uint64_t seed, uint32_t band_rows, rtiow_peer_frame_t* frame,
-                                           void* cuda_stream);
+RTIOW_API int rtiow_b200_render_peers(rtiow_scene_t* scene, const rtiow_camera_t* camera, uint32_t nx, uint32_t ny,
+                                      uint32_t ns, uint64_t seed, rtiow_peer_frame_t* frame, void* cuda_stream);
 
 /* Parity/debug: per-sample radiance before the fold, HOST memory,
  * (row_end-row_begin)*nx*ns*4 floats laid out [row][x][sample]{r,g,b,segments}. */

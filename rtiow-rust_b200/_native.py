@@ -72,7 +72,7 @@ ABI_SYMBOLS = ("rtiow_b200_abi_version", "rtiow_b200_build_flavour", "rtiow_b200
                "rtiow_b200_render_rows_device", "rtiow_b200_render_rows_strided_device", "rtiow_b200_render_samples", "rtiow_b200_ppm_quantise",
                "rtiow_b200_ppm_quantise_device", "rtiow_b200_render_ppm",
                "rtiow_b200_render_multi", "rtiow_b200_peer_frame_create", "rtiow_b200_peer_frame_export", "rtiow_b200_peer_frame_connect",
-               "rtiow_b200_peer_frame_ptr", "rtiow_b200_peer_frame_destroy", "rtiow_b200_render_rows_peers",
+               "rtiow_b200_peer_frame_ptr", "rtiow_b200_peer_frame_destroy", "rtiow_b200_render_peers",
                "rtiow_b200_get_stats", "rtiow_b200_set_tuning", "rtiow_b200_set_traversal", "rtiow_b200_set_specialisation")
 
 _abi = {}
@@ -110,7 +110,7 @@ def _declare(L):
     L.rtiow_b200_peer_frame_ptr.argtypes = [vp, C.POINTER(vp)]
     L.rtiow_b200_peer_frame_destroy.argtypes = [vp]
     L.rtiow_b200_peer_frame_destroy.restype = None
-    L.rtiow_b200_render_rows_peers.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, u32, vp, vp]
+    L.rtiow_b200_render_peers.argtypes = [vp, C.POINTER(CameraRec), u32, u32, u32, u64, vp, vp]
     L.rtiow_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.rtiow_b200_set_tuning.argtypes = [vp, u32, u32, u32, C.c_int]
     L.rtiow_b200_set_traversal.argtypes = [vp, C.c_int]

@@ -325,7 +325,6 @@ struct rtiow_scene {
 
     // tuning
     uint32_t cta_threads = 0, ctas_per_sm = 0, staging_mib = 0, sample_chunk = 0;
-    bool serpentine = true;        // RTIOW_B200_SERPENTINE=0: plain round-robin bands in multi-GPU renders
     bool force_global = false;
     uint32_t features = 0;         // scene_blob.hpp scene_features()
     bool specialise = true;        // use a kernel compiled for a subset of features when the scene allows (same image)
@@ -382,36 +381,48 @@ int check_render_args(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, ui
     if (nx == 0 || ny == 0 || ns == 0) return set_err(RTIOW_ERR_INVALID_ARG, "nx, ny and ns must be non-zero");
     if (r0 >= r1 || r1 > ny) return set_err(RTIOW_ERR_INVALID_ARG, "row range must satisfy row_begin < row_end <= ny");
     if (step == 0 || band == 0 || band > step) return set_err(RTIOW_ERR_INVALID_ARG, "need 1 <= band_rows <= row_step");
-    if (static_cast<uint64_t>(nx) * ny >= (1ull << 32)) return set_err(RTIOW_ERR_INVALID_ARG, "image too large");
+    if (nx > 65535u || ny > 65535u) return set_err(RTIOW_ERR_INVALID_ARG, "image too large (65535 x 65535 at most)");
     if (!(cam->time0 < cam->time1))  // rand's gen_range asserts low < high (camera.rs:55)
         return set_err(RTIOW_ERR_INVALID_ARG, "Uniform::sample_single called with low >= high (camera exposure)");
     return RTIOW_OK;
 }
 
-// Where a multi-GPU render puts its rows (rtiow_b200_render_rows_peers).
+// Where a multi-GPU render puts its pixels and which tiles of the frame are its own (rtiow_b200_render_peers).
 struct PeerTarget {
-    rtiow::FoldDst dst{};          // every rank's frame (the buffer of this epoch), rows at their position in the image
-    uint32_t row_begin_odd = 0;    // first row of this rank's band in the odd periods (serpentine deal)
+    rtiow::FoldDst dst{};          // every rank's frame (the buffer of this epoch)
+    uint32_t tile_first = 0, tile_step = 1;  // KParams: rank, number of ranks
 };
 constexpr unsigned long long kPeerTimeoutNs = 60ull * 1000ull * 1000ull * 1000ull;
 
-// Enqueue a full render of rows [r0, r1) into device buffer d_out (rgb floats, packed) — or, with `peers`, into
-// every rank's frame at the rows' image positions — and/or d_samples.
+// Enqueue a full render of rows [r0, r1) into device buffer d_out (rgb floats, packed) — or, with `peers`, of this
+// rank's tiles of those rows into every rank's frame — and/or d_samples.
 int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny, uint32_t ns, uint64_t seed,
                    uint32_t r0, uint32_t r1, float* d_out, float4* d_samples, cudaStream_t stream, uint32_t step = 1,
                    uint32_t band = 1, const PeerTarget* peers = nullptr) {
     CK(cudaSetDevice(s->device));
-    // bands of `band` rows starting at r0, r0 + step, ..., clipped to r1; with peers (serpentine deal, KParams) the odd
-    // bands start at r0_odd + step, r0_odd + 3 step, ...
-    const uint32_t r0_odd = peers ? peers->row_begin_odd : r0;
-    uint32_t n_rows = 0;
-    for (uint64_t b = 0;; ++b) {
-        const uint64_t begin = ((b & 1u) ? r0_odd : r0) + b * step;
-        if (begin >= r1) break;
-        n_rows += static_cast<uint32_t>(std::min<uint64_t>(band, r1 - begin));
-    }
-    const uint64_t npix64 = static_cast<uint64_t>(n_rows) * nx;
+    // bands of `band` rows starting at r0, r0 + step, ..., clipped to r1
+    const uint32_t n_full = (r1 - r0) / step, rest = (r1 - r0) - n_full * step;
+    const uint32_t n_rows = n_full * band + std::min(rest, band);
+    // 8x4-pixel tiles of the row block; this launch's share of them (all, or every tile_step-th for a rank of a peer render)
+    const uint32_t tiles_x = (nx + rtiow::kTileW - 1u) / rtiow::kTileW;
+    const uint32_t tiles_all = tiles_x * ((n_rows + rtiow::kTileH - 1u) / rtiow::kTileH);
+    const uint32_t tile_first = peers ? peers->tile_first : 0u, tile_step = peers ? peers->tile_step : 1u;
+    if (tile_first >= tiles_all) return RTIOW_OK;  // more ranks than tiles: nothing to render
+    const uint32_t n_groups = (tiles_all - tile_first + tile_step - 1u) / tile_step;
+    const uint64_t npix64 = static_cast<uint64_t>(n_groups) * 32u;  // staging slots (tile-major; edge tiles are padded)
+    if (npix64 >= (1ull << 32)) return set_err(RTIOW_ERR_INVALID_ARG, "image too large");
     const uint32_t npix = static_cast<uint32_t>(npix64);
+    uint64_t real_pix = static_cast<uint64_t>(n_rows) * nx;  // (statistics)
+    if (peers) {
+        real_pix = npix64;
+        const uint32_t edge_w = nx % rtiow::kTileW, edge_h = n_rows % rtiow::kTileH;
+        if (edge_w || edge_h)  // the tiles on the right / bottom edge are partly outside the frame
+            for (uint32_t t = tile_first; t < tiles_all; t += tile_step) {
+                const uint32_t w = (t % tiles_x == tiles_x - 1u && edge_w) ? edge_w : rtiow::kTileW;
+                const uint32_t h = (t / tiles_x == tiles_all / tiles_x - 1u && edge_h) ? edge_h : rtiow::kTileH;
+                real_pix -= 32u - w * h;
+            }
+    }
     Workspace& W = *s->ws;
     CK(W.order_after_last_render(stream));
     // Per-sample staging budget.  Automatic: up to 56 GiB, at most 70 % of what is free — a B200 has 180 GB and a
@@ -485,14 +496,13 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var.fn, var.threads, dyn_smem));
     if (occ < 1) return set_err(RTIOW_ERR_CUDA, "render kernel does not fit on an SM");
     if (s->ctas_per_sm) occ = std::min<int>(occ, static_cast<int>(s->ctas_per_sm));
-    const uint32_t tiles_x = (nx + rtiow::kTileW - 1u) / rtiow::kTileW;
-    const uint32_t n_groups = tiles_x * ((n_rows + rtiow::kTileH - 1u) / rtiow::kTileH);  // 8x4-pixel tiles
     uint32_t grid = static_cast<uint32_t>(s->sm_count) * static_cast<uint32_t>(occ);
     const uint32_t warps_per_cta = static_cast<uint32_t>(var.threads) / 32u;
     // no more CTAs than there is work for: a warp takes at least one unit (one sample of one tile)
     const uint64_t min_units = static_cast<uint64_t>(n_groups) * std::min(s_pass, ns);
     grid = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(grid, (min_units + warps_per_cta - 1) / warps_per_cta)));
 
+    const rtiow::TileMap tile_map{nx, n_rows, tiles_x, tile_first, tile_step};
     KParams P{};
     P.blob = B.d;
     P.blob_bytes = B.bytes;
@@ -500,8 +510,8 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     P.off_tex = B.lay.off_tex; P.off_pvecs = B.lay.off_pvecs; P.off_pperm = B.lay.off_pperm;
     P.off_fnodes = B.lay.off_fnodes;
     std::memcpy(P.cam, cam, sizeof(float) * 21);
-    P.nx = nx; P.ny = ny; P.row_begin = r0; P.row_begin_odd = r0_odd; P.n_rows = n_rows; P.row_step = step; P.row_band = band;
-    P.npix = npix; P.tiles_x = tiles_x;
+    P.nx = nx; P.ny = ny; P.row_begin = r0; P.n_rows = n_rows; P.row_step = step; P.row_band = band;
+    P.npix = npix; P.tiles_x = tiles_x; P.tile_first = tile_first; P.tile_step = tile_step;
     P.key0 = static_cast<uint32_t>(seed); P.key1 = static_cast<uint32_t>(seed >> 32);
     P.bg_kind = s->bg_kind;
     std::memcpy(P.bg0, s->bg0, 12); std::memcpy(P.bg1, s->bg1, 12);
@@ -608,7 +618,7 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
         if (d_samples) {
             const uint64_t n = npix64 * P.s_count;
             rtiow::export_samples_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
-                P.staging, d_samples, npix, P.s_begin, P.s_count, ns);
+                P.staging, d_samples, tile_map, npix, P.s_begin, P.s_count, ns);
             CK(cudaGetLastError());
             ++launches;
         }
@@ -616,12 +626,11 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
             rtiow::FoldDst dst{};
             if (peers) {
                 dst = peers->dst;
-                dst.nx = nx; dst.row_begin = r0; dst.row_begin_odd = r0_odd; dst.row_step = step; dst.row_band = band;
-                dst.image_rows = 1u;
             } else {
                 dst.p[0] = d_out;
                 dst.n = 1u;
             }
+            dst.map = tile_map;
             rtiow::fold_kernel<<<(npix + 255u) / 256u, 256, 0, stream>>>(
                 P.staging, static_cast<float4*>(SL.accum.p), dst, npix, P.s_count, pass == 0, pass + 1 == n_pass,
                 static_cast<float>(ns), W.d_segs);
@@ -634,7 +643,7 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     }
     CK(W.mark_render_end(stream));
     s->stats = rtiow_stats_t{};
-    s->stats.samples = npix64 * ns;
+    s->stats.samples = real_pix * ns;
     s->stats.kernel_launches = launches;
     s->stats.passes = n_pass;
     s->stats.scene_in_smem = smem ? 1u : 0u;
@@ -728,7 +737,6 @@ int rtiow_b200_scene_create(const rtiow_scene_desc_t* d, int device, rtiow_scene
     if (const char* env = std::getenv("RTIOW_B200_UNIT_ORDER")) s->bottom_first = std::atoi(env) != 0;
     if (const char* env = std::getenv("RTIOW_B200_PHASE_SYNC")) s->phase_sync = std::max(0, std::atoi(env));
     if (const char* env = std::getenv("RTIOW_B200_PHASE_GROUP")) s->phase_group_env = static_cast<uint32_t>(std::max(1, std::atoi(env)));
-    if (const char* env = std::getenv("RTIOW_B200_SERPENTINE")) s->serpentine = std::atoi(env) != 0;
     if (const char* env = std::getenv("RTIOW_B200_SAMPLE_CHUNK")) s->sample_chunk = static_cast<uint32_t>(std::max(0, std::atoi(env)));
     {   // build + upload the blob of the selected traversal now, so that render calls only launch
         const rtiow::BlobMode mode = s->traversal == RTIOW_TRAVERSAL_REFERENCE_ORDER ? rtiow::kBlobReferenceOrder
@@ -912,21 +920,20 @@ constexpr uint32_t kPeerMagic = 0x52543230u;
 
 uint64_t my_pid();
 
-// Renders rank `pf->rank`'s bands of `band` rows into the frames listed in `dst_ranks` (a bit mask) and, if `handshake`,
+// Renders rank `pf->rank`'s tiles of the frame into the frames listed in `dst_ranks` (a bit mask) and, if `handshake`,
 // ends with the barrier that makes the frame whole on every rank.
-int render_bands(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny, uint32_t ns, uint64_t seed, uint32_t band,
+int render_share(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny, uint32_t ns, uint64_t seed,
                  rtiow_peer_frame* pf, uint32_t dst_mask, bool handshake, cudaStream_t stream) {
     if (!pf->connected && pf->n_ranks > 1) return set_err(RTIOW_ERR_INVALID_ARG, "peer frame is not connected");
     if (pf->nx != nx || pf->ny != ny) return set_err(RTIOW_ERR_INVALID_ARG, "peer frame has another size");
     if (s->device != pf->device) return set_err(RTIOW_ERR_INVALID_ARG, "scene and peer frame live on different devices");
     if (*pf->timed_out) return set_err(RTIOW_ERR_CUDA, "a peer did not arrive within the time-out in an earlier multi-GPU render");
     CK(cudaSetDevice(s->device));
-    // bands are dealt in serpentine order: ranks 0..G-1 in even periods of G bands, G-1..0 in odd ones — in the reference's
-    // scenes cost grows from the top of the frame (sky, one segment) to the bottom, and with a plain round-robin the last
-    // rank's rows are all 4 (G-1) rows further down than the first's: 1.6-2.7 % more work on 8 GPUs (profiles/r02)
-    const uint32_t G = pf->n_ranks, r0 = pf->rank * band, step = G * band;
+    // The frame's 8x4-pixel tiles are dealt round-robin: rank r renders tiles r, r + G, ... of the whole frame (KParams).
+    const uint32_t G = pf->n_ranks;
     PeerTarget T{};
-    T.row_begin_odd = s->serpentine ? (G - 1u - pf->rank) * band : r0;
+    T.tile_first = pf->rank;
+    T.tile_step = G;
     const unsigned int epoch = ++pf->epoch;
     rtiow::PeerFlags arrived{};
     for (uint32_t q = 0; q < G; ++q) {
@@ -936,8 +943,8 @@ int render_bands(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint32_
     arrived.n = G;
     // No wait before the fold: it overwrites the peers' copies of frame epoch - 2, and this stream is already past the
     // barrier of epoch - 1, which every peer entered after its reads of that frame (aux_kernels.cuh).
-    if (r0 < ny)  // (more ranks than bands: nothing to render, but the barrier still runs)
-        if (int rc = enqueue_render(s, cam, nx, ny, ns, seed, r0, ny, nullptr, nullptr, stream, step, band, &T)) return rc;
+    // (more ranks than tiles: nothing to render, but the barrier still runs)
+    if (int rc = enqueue_render(s, cam, nx, ny, ns, seed, 0, ny, nullptr, nullptr, stream, 1, 1, &T)) return rc;
     if (handshake && G > 1) {  // my rows are in every frame -> tell everybody; the frame is whole once everybody has told me
         rtiow::peer_barrier_kernel<<<1, 32, 0, stream>>>(arrived, pf->rank, epoch, kPeerTimeoutNs, pf->timed_out);
         CK(cudaGetLastError());
@@ -1055,12 +1062,11 @@ void MultiFrames::destroy() {
 }  // namespace
 extern "C" {
 
-int rtiow_b200_render_rows_peers(rtiow_scene_t* s, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny, uint32_t ns, uint64_t seed,
-                                 uint32_t band_rows, rtiow_peer_frame_t* pf, void* cuda_stream) {
+int rtiow_b200_render_peers(rtiow_scene_t* s, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny, uint32_t ns, uint64_t seed,
+                                 rtiow_peer_frame_t* pf, void* cuda_stream) {
     if (!pf) return set_err(RTIOW_ERR_INVALID_ARG, "null argument");
-    if (int rc = check_render_args(s, cam, nx, ny, ns, 0, ny, pf, pf->n_ranks * std::max(1u, band_rows), std::max(1u, band_rows))) return rc;
-    if (band_rows == 0) return set_err(RTIOW_ERR_INVALID_ARG, "band_rows must be non-zero");
-    return render_bands(s, cam, nx, ny, ns, seed, band_rows, pf, (1u << pf->n_ranks) - 1u, true, static_cast<cudaStream_t>(cuda_stream));
+    if (int rc = check_render_args(s, cam, nx, ny, ns, 0, ny, pf)) return rc;
+    return render_share(s, cam, nx, ny, ns, seed, pf, (1u << pf->n_ranks) - 1u, true, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int rtiow_b200_render_multi(rtiow_scene_t* const* scenes, int ngpus, const rtiow_camera_t* cam, uint32_t nx, uint32_t ny, uint32_t ns,
@@ -1073,10 +1079,8 @@ int rtiow_b200_render_multi(rtiow_scene_t* const* scenes, int ngpus, const rtiow
     for (int g = 0; g < ngpus; ++g)
         for (int h = 0; h < g; ++h)
             if (scenes[g]->device == scenes[h]->device) return set_err(RTIOW_ERR_INVALID_ARG, "two scene handles on the same device");
-    // bands of 4 scanlines (the height of the kernel's work tiles) dealt round-robin: every GPU gets the same mix of cheap
-    // and expensive rows; single rows when the frame is too small for that to balance
+    // the frame's 8x4-pixel tiles are dealt round-robin (render_share): every GPU gets the same mix of cheap and expensive pixels
     const uint32_t G = static_cast<uint32_t>(ngpus);
-    const uint32_t band = ny >= 8u * rtiow::kTileH * G ? rtiow::kTileH : 1u;
     // the devices' frames (GPU 0's is the one that gets assembled) are kept between calls of the same shape
     std::vector<int> devices;
     for (uint32_t g = 0; g < G; ++g) devices.push_back(scenes[g]->device);
@@ -1109,10 +1113,10 @@ int rtiow_b200_render_multi(rtiow_scene_t* const* scenes, int ngpus, const rtiow
         mf = &g_multi_cache.back();
     }
     std::vector<rtiow_peer_frame_t*>& pf = mf->pf;
-    // every GPU renders its bands and its fold stores them straight into GPU 0's frame (the only consumer here); one host
+    // every GPU renders its tiles and its fold stores them straight into GPU 0's frame (the only consumer here); one host
     // thread drives all of them, the devices run concurrently
     for (uint32_t g = 0; g < G && rc == RTIOW_OK; ++g) {
-        rc = render_bands(scenes[g], cam, nx, ny, ns, seed, band, pf[g], 1u, false, scenes[g]->ws->stream);
+        rc = render_share(scenes[g], cam, nx, ny, ns, seed, pf[g], 1u, false, scenes[g]->ws->stream);
         if (rc == RTIOW_OK && cudaEventRecord(pf[g]->done_ev, scenes[g]->ws->stream) != cudaSuccess) rc = set_err(RTIOW_ERR_CUDA, "cudaEventRecord");
         if (rc == RTIOW_OK && scenes[g]->ws->mark_render_end(scenes[g]->ws->stream) != cudaSuccess) rc = set_err(RTIOW_ERR_CUDA, "cudaEventRecord");
     }

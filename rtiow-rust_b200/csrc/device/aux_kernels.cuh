@@ -7,21 +7,28 @@ namespace rtiow {
 
 // ------------------------------------------------------------------------------------------------
 // Fold kernel: `(0..ns).map(..).sum()` then `col / ns as f32` (lib.rs:365-374, vec3.rs:195-203).
-// One thread per pixel walks its samples in order; staging is [sample][pixel] so a warp reads
-// 512 contiguous bytes per sample.
+// One thread per pixel walks its samples in order; staging is [sample][tile][pixel of the tile] (KParams), so a warp
+// reads 512 contiguous bytes per sample and writes four 96-byte row pieces.
 //
 // Where the finished pixel goes: to `n` frames (this GPU's and, through NVLink peer pointers, the
-// other GPUs': the fold IS the framebuffer exchange, there is no all-gather behind it), either packed
-// (pixel p of the rendered row block -> p) or at the row's position in the whole image (packed row r
-// = row r % row_band of band b = r / row_band, which starts at image row (b odd ? row_begin_odd : row_begin) + b * row_step;
-// KParams in path_logic.cuh).
+// other GPUs': the fold IS the framebuffer exchange, there is no all-gather behind it), at packed row r
+// of the row block — the whole image in a multi-GPU peer render, where every rank folds its own tiles of it.
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxFoldDst = 16;
+struct TileMap {  // KParams' tiling of the row block
+    uint32_t nx, n_rows, tiles_x, tile_first, tile_step;
+    // staging pixel p -> column x and packed row r; false for the pixels of edge tiles that lie outside the block
+    __device__ __forceinline__ bool locate(uint32_t p, uint32_t& x, uint32_t& r) const {
+        const uint32_t tile = (p >> 5) * tile_step + tile_first, ty = tile / tiles_x;
+        x = (tile - ty * tiles_x) * 8u + (p & 7u);
+        r = ty * 4u + ((p >> 3) & 3u);
+        return x < nx && r < n_rows;
+    }
+};
 struct FoldDst {
     float* p[kMaxFoldDst];
     uint32_t n;
-    uint32_t image_rows;  // 0: packed; 1: rows land at their position in the ny x nx image
-    uint32_t nx, row_begin, row_begin_odd, row_step, row_band;
+    TileMap map;
 };
 
 __global__ void __launch_bounds__(256) fold_kernel(const float4* __restrict__ staging, float4* __restrict__ accum,
@@ -30,7 +37,8 @@ __global__ void __launch_bounds__(256) fold_kernel(const float4* __restrict__ st
                                                    unsigned long long* __restrict__ seg_total) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     float segs = 0.f;
-    if (p < npix) {
+    uint32_t x = 0, r = 0;
+    if (p < npix && dst.map.locate(p, x, r)) {
         float4 acc = first_pass ? make_float4(0.f, 0.f, 0.f, 0.f) : accum[p];
         for (uint32_t s = 0; s < s_count; ++s) {
             const float4 v = __ldcs(staging + static_cast<size_t>(s) * npix + p);
@@ -40,13 +48,7 @@ __global__ void __launch_bounds__(256) fold_kernel(const float4* __restrict__ st
             segs += v.w;
         }
         if (last_pass) {
-            size_t o = 3u * static_cast<size_t>(p);
-            if (dst.image_rows) {
-                const uint32_t r = p / dst.nx, x = p - r * dst.nx;
-                const uint32_t band = r / dst.row_band;
-                const uint32_t row = ((band & 1u) ? dst.row_begin_odd : dst.row_begin) + band * dst.row_step + (r - band * dst.row_band);
-                o = 3u * (static_cast<size_t>(row) * dst.nx + x);
-            }
+            const size_t o = 3u * (static_cast<size_t>(r) * dst.map.nx + x);
             const float cr = acc.x / ns_f, cg = acc.y / ns_f, cb = acc.z / ns_f;
             for (uint32_t k = 0; k < dst.n; ++k) {
                 float* out = dst.p[k] + o;
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(256) fold_kernel(const float4* __restrict__ st
 }
 
 // ------------------------------------------------------------------------------------------------
-// Cross-GPU hand-shake of the peer-store exchange (rtiow_b200_render_rows_peers): ONE barrier per frame.
+// Cross-GPU hand-shake of the peer-store exchange (rtiow_b200_render_peers): ONE barrier per frame.
 // Every rank owns a flag array in its peer-visible allocation; flags[q] is written by rank q only.
 //   arrive: after everything enqueued before this kernel on the stream (the fold that stored my rows into every rank's
 //           frame), publish `epoch` into MY slot of every rank's array (system-scope release);
@@ -103,14 +105,16 @@ __global__ void peer_barrier_kernel(const __grid_constant__ PeerFlags flags, uin
     }
 }
 
-// Per-sample export for parity debugging: staging [s][pix] -> out [pix][ns_total][4]
+// Per-sample export for parity debugging: staging [s][tile][pixel] -> out [row][x][ns_total][4]
 __global__ void __launch_bounds__(256) export_samples_kernel(const float4* __restrict__ staging, float4* __restrict__ out,
-                                                             uint32_t npix, uint32_t s_begin, uint32_t s_count,
+                                                             const TileMap map, uint32_t npix, uint32_t s_begin, uint32_t s_count,
                                                              uint32_t ns_total) {
     const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= static_cast<size_t>(npix) * s_count) return;
     const uint32_t s = static_cast<uint32_t>(idx / npix), p = static_cast<uint32_t>(idx % npix);
-    out[static_cast<size_t>(p) * ns_total + s_begin + s] = staging[idx];
+    uint32_t x, r;
+    if (!map.locate(p, x, r)) return;
+    out[(static_cast<size_t>(r) * map.nx + x) * ns_total + s_begin + s] = staging[idx];
 }
 
 // print_ppm's quantiser (lib.rs:344-361): sqrt, then ((255.99 * x) as i32).max(0).min(255)

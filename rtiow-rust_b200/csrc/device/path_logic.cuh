@@ -38,13 +38,15 @@ struct KParams {
     uint32_t off_nodes, off_frames, off_ops, off_mats, off_tex, off_pvecs, off_pperm;
     uint32_t off_fnodes;        // conservative-test nodes (accel_build.hpp FastNode); 0 = none
     float cam[21];              // rtiow_camera_t
-    // packed row r is row r % row_band of band b = r / row_band, which starts at image row (b odd ? row_begin_odd : row_begin)
-    // + b * row_step (n_rows packed rows).  row_begin_odd != row_begin deals the bands to the ranks of a multi-GPU render in
-    // serpentine order — rank r takes band r of even periods and band G-1-r of odd ones — which cancels the top-to-bottom
-    // cost gradient of a frame (sky above, ground below) between the ranks.
-    uint32_t nx, ny, row_begin, row_begin_odd, n_rows, row_step, row_band;
+    // packed row r is image row row_begin + (r / row_band) * row_step + r % row_band (n_rows of them)
+    uint32_t nx, ny, row_begin, n_rows, row_step, row_band;
+    // The n_rows x nx row block is cut into 8x4-pixel tiles, tiles_x per tile row; this launch renders tiles tile_first,
+    // tile_first + tile_step, ... (n_groups of them).  One GPU: all of them (0, 1).  Rank r of a G-GPU peer render: (r, G)
+    // over the WHOLE frame — every rank's tiles are spread evenly over the image, so the ranks' work differs by well under
+    // a per cent where whole bands of rows differed by 6 % (the big spheres of book-1 span only a few band periods).
+    uint32_t tile_first, tile_step;
     uint32_t s_begin, s_count;  // samples [s_begin, s_begin + s_count) of every pixel in this pass
-    uint32_t npix, tiles_x;     // the row block is cut into 8x4-pixel tiles, tiles_x per tile row
+    uint32_t npix, tiles_x;     // npix = 32 * n_groups: the staging buffer is tile-major, [sample][tile of this launch][pixel of the tile]
     // Work unit = a chunk of samples of one tile, in two sizes: units [0, n_big_units) are chunks of s_chunk samples
     // covering samples [0, s_tail_begin) of every tile, the rest chunks of s_chunk_tail samples covering the remainder —
     // large units while there is plenty of work (one atomic and one coherent batch of rays per 8 x 32 samples), small ones
@@ -452,7 +454,7 @@ static RT_HD_NOINLINE float shutter_time_retry(Rng rng, float scale, float toff,
 // (x, r) = column and packed row of st.pix.
 RT_HD void generate_camera_ray(const KParams& P, PathState& st, uint32_t x, uint32_t r) {
     const uint32_t band = r / P.row_band;
-    const uint32_t y = P.ny - 1u - (((band & 1u) ? P.row_begin_odd : P.row_begin) + band * P.row_step + (r - band * P.row_band));  // (0..ny).rev()  lib.rs:326-330
+    const uint32_t y = P.ny - 1u - (P.row_begin + band * P.row_step + (r - band * P.row_band));  // (0..ny).rev()  lib.rs:326-330
     st.rng.pixel = y * P.nx + x;
     st.rng.sample = st.samp;
     const U4 cw = st.rng.block(0u, PURPOSE_CAMERA, 0u);

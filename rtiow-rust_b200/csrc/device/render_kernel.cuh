@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     // ---- warp-uniform job pool: the samples of one 8x4-pixel tile ------------------------------
-    uint32_t pool_x0 = 0, pool_r0 = 0, pool_next = 0, pool_end = 0, pool_s0 = 0;
+    uint32_t pool_xy = 0, pool_pix0 = 0, pool_next = 0, pool_end = 0, pool_s0 = 0;  // pool_xy: first packed row << 16 | first column
     bool exhausted = false;
 
     // ---- per-lane path state ------------------------------------------------------------------
@@ -102,10 +102,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
                 if (need && !fresh && my_rank < avail) {
                     // job = sample-major over the tile: 32 neighbouring pixels of one sample first
                     const uint32_t job = pool_next + my_rank;
-                    const uint32_t x = pool_x0 + (job & (kTileW - 1u)), r = pool_r0 + ((job >> kTileWLog2) & (kTileH - 1u));
+                    const uint32_t x = (pool_xy & 0xffffu) + (job & (kTileW - 1u)), r = (pool_xy >> 16) + ((job >> kTileWLog2) & (kTileH - 1u));
                     if (x < P.nx && r < P.n_rows) {  // tiles on the right / bottom edge are partly outside
                         st.samp = P.s_begin + pool_s0 + (job >> 5);
-                        st.pix = r * P.nx + x;
+                        st.pix = pool_pix0 + (job & 31u);  // tile-major staging: a tile's 32 pixels of one sample are 512 contiguous bytes
                         fresh_x = x;
                         fresh_r = r;
                         fresh = true;
@@ -135,9 +135,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
                     s_n = P.s_count - pool_s0 < P.s_chunk_tail ? P.s_count - pool_s0 : P.s_chunk_tail;
                 }
                 if (P.bottom_first != 0u) g = P.n_groups - 1u - g;
-                const uint32_t ty = g / P.tiles_x;
-                pool_x0 = (g - ty * P.tiles_x) * kTileW;
-                pool_r0 = ty * kTileH;
+                pool_pix0 = g * 32u;
+                const uint32_t tile = g * P.tile_step + P.tile_first, ty = tile / P.tiles_x;
+                pool_xy = ((ty * kTileH) << 16) | ((tile - ty * P.tiles_x) * kTileW);
                 pool_next = 0u;
                 pool_end = 32u * s_n;
             }

@@ -17,7 +17,7 @@ Two ways to exchange the rows:
 
   peer stores (default)  the kernel that finishes a pixel (the in-order sample fold) stores it straight into EVERY
                          rank's frame through NVLink peer pointers, at the row's final position
-                         (rtiow_b200_render_rows_peers): the exchange is fused into the fold, no collective is called
+                         (rtiow_b200_render_peers): the exchange is fused into the fold, no collective is called
                          on the data path, only the ranks' 128-byte frame handles are exchanged once at set-up.
   NCCL                   one all_gather_into_tensor of the packed rows (+ one strided de-interleave copy for the
                          interleaved partition): BASELINE.json's wording, kept as the cross-check and fallback.
@@ -71,7 +71,11 @@ class RowShard:
         b = sum(self.counts[:r])
         return list(range(b, b + self.counts[r]))
 
-    def describe(self):
+    def describe(self, tiles=False):
+        """`tiles`: the peer-store exchange deals 8x4-pixel tiles instead (rank r: tiles r, r + G, ... of the whole frame;
+        rtiow_b200_render_peers) and the library assembles the frame."""
+        if tiles:
+            return f"{max(self.counts)} rows' worth x {self.world_size} rank(s), 8x4-pixel tiles dealt round-robin (rank r: tiles r, r+G, ...)"
         kind = (f"interleaved bands of {self.band} row(s) (rank r: bands r, r+G, ...)" if self.interleaved else "contiguous blocks")
         return f"{max(self.counts)} rows x {self.world_size} rank(s), {kind}"
 
@@ -137,11 +141,11 @@ class PeerFrame:
             self._views[ptr.value] = torch.as_tensor(_DeviceArray(ptr.value, (self.ny, self.nx, 3)), device=f"cuda:{self.device_index}")
         self.frame = self._views[ptr.value]
 
-    def render(self, nx, ny, ns, camera, world, band_rows, seed=api.DEFAULT_SEED, stream=None):
-        """This rank's share (rtiow_b200_render_rows_peers), enqueued on `stream` (default: current)."""
+    def render(self, nx, ny, ns, camera, world, seed=api.DEFAULT_SEED, stream=None):
+        """This rank's share (rtiow_b200_render_peers), enqueued on `stream` (default: current)."""
         import torch
         s = stream if stream is not None else torch.cuda.current_stream(self.device_index)
-        api._check(self.lib.rtiow_b200_render_rows_peers(world.gpu(self.device_index), C.byref(camera.rec), nx, ny, ns, seed, band_rows,
+        api._check(self.lib.rtiow_b200_render_peers(world.gpu(self.device_index), C.byref(camera.rec), nx, ny, ns, seed,
                                                          self.h, C.c_void_p(s.cuda_stream)), self.lib)
         self._latest()
 
@@ -181,7 +185,7 @@ class ShardBuffers:
             self._frame = None
             self.mine = self.parts = None
             self.exchange = ("fused into the sample fold: every finished row is stored into every rank's frame through NVLink peer "
-                             "pointers (rtiow_b200_render_rows_peers); no collective on the data path")
+                             "pointers (rtiow_b200_render_peers); no collective on the data path")
             return
         self._frame = torch.empty((ny, nx, 3), dtype=torch.float32, device=device)
         self.exchange = "none (one rank)" if shard.world_size == 1 else "one NCCL all_gather_into_tensor of the packed rows" + (
@@ -213,7 +217,7 @@ def render_sharded_device(nx, ny, ns, camera, world, bufs, seed=api.DEFAULT_SEED
     import torch.distributed as dist
     sh = bufs.shard
     if bufs.peer is not None:
-        bufs.peer.render(nx, ny, ns, camera, world, sh.band, seed=seed)
+        bufs.peer.render(nx, ny, ns, camera, world, seed=seed)
         return bufs.frame
     if sh.n_rows > 0:
         api.render_rows_device(nx, ny, ns, camera, world, bufs.mine, (sh.begin, sh.end), seed=seed, row_step=sh.step, row_band=sh.band)

@@ -189,8 +189,8 @@ extern "C" {
     pub fn rtiow_b200_peer_frame_connect(frame: *mut rtiow_peer_frame_t, handles: *const u8) -> c_int;
     pub fn rtiow_b200_peer_frame_ptr(frame: *mut rtiow_peer_frame_t, d_frame: *mut *mut f32) -> c_int;
     pub fn rtiow_b200_peer_frame_destroy(frame: *mut rtiow_peer_frame_t);
-    pub fn rtiow_b200_render_rows_peers(scene: *mut rtiow_scene_t, camera: *const rtiow_camera_t, nx: u32, ny: u32, ns: u32,
-                                        seed: u64, band_rows: u32, frame: *mut rtiow_peer_frame_t,
+    pub fn rtiow_b200_render_peers(scene: *mut rtiow_scene_t, camera: *const rtiow_camera_t, nx: u32, ny: u32, ns: u32,
+                                        seed: u64, frame: *mut rtiow_peer_frame_t,
                                         cuda_stream: *mut c_void) -> c_int;
     pub fn rtiow_b200_render_samples(scene: *mut rtiow_scene_t, camera: *const rtiow_camera_t, nx: u32, ny: u32, ns: u32,
                                      seed: u64, row_begin: u32, row_end: u32, out_samples: *mut f32) -> c_int;

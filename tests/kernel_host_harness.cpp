@@ -37,7 +37,7 @@ static int harness_render_impl(const rtiow_scene_desc_t* desc, const rtiow_camer
     std::memcpy(P.cam, cam, sizeof(float) * 21);
     if (row_step == 0) row_step = 1;
     if (row_band == 0) row_band = 1;
-    P.nx = nx; P.ny = ny; P.row_begin = P.row_begin_odd = row_begin; P.row_step = row_step; P.row_band = row_band;
+    P.nx = nx; P.ny = ny; P.row_begin = row_begin; P.row_step = row_step; P.row_band = row_band;
     P.n_rows = 0;  // bands of row_band rows starting at row_begin, +step, ... clipped to row_end
     for (uint32_t b = row_begin; b < row_end; b += row_step) P.n_rows += row_end - b < row_band ? row_end - b : row_band;
     P.s_begin = 0; P.s_count = ns;

@@ -312,7 +312,7 @@ def test_band_shards_of_every_world_size_assemble_to_the_same_bits(G):
 
 
 def test_peer_store_exchange_two_ranks_on_one_gpu():
-    """The multi-GPU exchange (rtiow_b200_render_rows_peers: the fold stores every finished row into every rank's frame,
+    """The multi-GPU exchange (rtiow_b200_render_peers: the fold stores every finished row into every rank's frame,
     then one barrier) with both ranks on this one GPU: two scene handles, two streams, two peer frames mapped into each
     other.  Both frames must hold the whole image, bit-identical to the single-launch frame, call after call."""
     import torch
@@ -325,11 +325,10 @@ def test_peer_store_exchange_two_ranks_on_one_gpu():
     for f in frames:
         f.connect([g.handle for g in frames])
     streams = [torch.cuda.Stream() for _ in range(G)]
-    band = rdist.RowShard(ny, 0, G).band
     for seed in (1, 2, 3):
         want = full if seed == 1 else R.par_cast(nx, ny, ns, cam, worlds[0][0], seed=seed).rgb
         for r in range(G):
-            frames[r].render(nx, ny, ns, cam, worlds[r][0], band, seed=(0xDEADBEEF if seed == 1 else seed), stream=streams[r])
+            frames[r].render(nx, ny, ns, cam, worlds[r][0], seed=(0xDEADBEEF if seed == 1 else seed), stream=streams[r])
         for st in streams:
             st.synchronize()
         for r in range(G):
@@ -341,7 +340,7 @@ def test_peer_store_exchange_two_ranks_on_one_gpu():
     snaps = [[None] * len(seeds) for _ in range(G)]
     for i, seed in enumerate(seeds):
         for r in range(G):
-            frames[r].render(nx, ny, ns, cam, worlds[r][0], band, seed=seed, stream=streams[r])
+            frames[r].render(nx, ny, ns, cam, worlds[r][0], seed=seed, stream=streams[r])
             with torch.cuda.stream(streams[r]):
                 snaps[r][i] = frames[r].frame.clone()
     for st in streams:
