@@ -13,6 +13,8 @@
 #include <vector>
 
 #include "../../../include/rtiow_b200.h"
+#include <cub/device/device_radix_sort.cuh>
+
 #include "../device/aux_kernels.cuh"
 #include "kernel_table.hpp"
 #include "scene_blob.hpp"
@@ -62,12 +64,21 @@ struct Workspace {
     // long paths are still running (enqueue_render).  Frames whose staging is large use slot 0 only.
     struct Slot {
         DevBuf staging, accum;
-        unsigned int* d_counter = nullptr;
         cudaStream_t stream = nullptr;
         cudaEvent_t render_done = nullptr, fold_done = nullptr;
         bool fold_recorded = false;
-    } slot[2];
-    uint32_t next_slot = 0;
+        // Tile order of the slot's next render: after a render's last fold its tiles are sorted by the longest path found
+        // in each (DevBufs: keys in reverse tile order, sorted keys, the values n-1 .. 0, the sorted values = the order,
+        // CUB's scratch).  `order_shape` says which launch shape the order belongs to.  tiles_in and tile_order each start
+        // with a 128-byte header that holds the launch's unit counter: the kernel finds the order behind its counter
+        // (KParams), whichever of the two a launch uses.
+        DevBuf longest, longest_sorted, tiles_in, tile_order, sort_tmp;
+        uint64_t order_shape[4] = {0, 0, 0, 0};
+        bool order_valid = false;
+        uint32_t order_age = 0;   // renders since the order was learnt
+        uint32_t default_order_n = 0;  // tiles_in holds the default order of this many tiles (x 2 + direction)
+    } slot[4];
+    uint32_t next_slot = 0, n_slots = 2;
     DevBuf out, samples;
     DevBuf scene_blob[3];  // device image of the owning scene, by blob mode
     unsigned long long* d_segs = nullptr;
@@ -107,7 +118,6 @@ struct Workspace {
         cudaError_t e;
         if ((e = cudaEventCreateWithFlags(&busy, cudaEventDisableTiming)) != cudaSuccess) return e;
         for (Slot& sl : slot) {
-            if ((e = cudaMalloc(reinterpret_cast<void**>(&sl.d_counter), sizeof(unsigned int))) != cudaSuccess) return e;
             if ((e = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
             if ((e = cudaEventCreateWithFlags(&sl.render_done, cudaEventDisableTiming)) != cudaSuccess) return e;
             if ((e = cudaEventCreateWithFlags(&sl.fold_done, cudaEventDisableTiming)) != cudaSuccess) return e;
@@ -123,7 +133,7 @@ struct Workspace {
         for (Slot& sl : slot) {
             if (sl.stream) cudaStreamSynchronize(sl.stream);
             sl.staging.release(); sl.accum.release();
-            if (sl.d_counter) cudaFree(sl.d_counter);
+            sl.longest.release(); sl.longest_sorted.release(); sl.tiles_in.release(); sl.tile_order.release(); sl.sort_tmp.release();
             if (sl.render_done) cudaEventDestroy(sl.render_done);
             if (sl.fold_done) cudaEventDestroy(sl.fold_done);
             if (sl.stream) cudaStreamDestroy(sl.stream);
@@ -240,6 +250,7 @@ Workspace* ws_acquire(int device, cudaError_t* err) {
             if (g_ws_cache[i]->device == device) {
                 Workspace* w = g_ws_cache[i];
                 g_ws_cache.erase(g_ws_cache.begin() + static_cast<std::ptrdiff_t>(i));
+                for (Workspace::Slot& sl : w->slot) sl.order_valid = false;  // a tile order belongs to the scene that produced it
                 return w;
             }
     }
@@ -322,6 +333,11 @@ struct rtiow_scene {
 
     Workspace* ws = nullptr;
     uint32_t events_used = 0;
+#ifdef RT_CTA_TIMELINE
+    std::vector<std::pair<unsigned long long*, uint32_t>> cta_timelines;
+#endif
+    bool timeline_on = false;                 // RTIOW_B200_TIMELINE=1: keep every launch's events, print them at scene_destroy
+    std::vector<cudaEvent_t> timeline;        // per pass: render start / end (slot stream), fold start / end (caller's stream)
 
     // tuning
     uint32_t cta_threads = 0, ctas_per_sm = 0, staging_mib = 0, sample_chunk = 0;
@@ -333,6 +349,7 @@ struct rtiow_scene {
     bool pipeline = true;          // consecutive renders alternate between two pipeline slots (RTIOW_B200_PIPELINE=0: one)
     bool fuse_prisms = true;       // six-Rect rect_prism runs become one prism record (RTIOW_B200_FUSE_PRISMS=0: keep the rects)
     bool bottom_first = true;      // unit order (RTIOW_B200_UNIT_ORDER=0: top rows first)
+    bool order_hint = true;        // RTIOW_B200_ORDER_HINT=0: never reorder the tiles by the previous render's path lengths
     int phase_sync = -1;           // -1 = automatic (RTIOW_B200_PHASE_SYNC, read once at scene_create)
     uint32_t phase_group_env = 0;  // RTIOW_B200_PHASE_GROUP, 0 = automatic
 
@@ -430,7 +447,7 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     // Which pipeline slot: alternate for frames whose staging is small (a kernel of a few milliseconds, where the ~0.15 ms
     // in which the last long paths finish is worth hiding behind the next render); big frames stay on slot 0.
     const bool pipelined = s->pipeline && npix64 * ns * 16 <= (4ull << 30);
-    const uint32_t slot_id = pipelined ? (W.next_slot++ & 1u) : 0u;
+    const uint32_t slot_id = pipelined ? (W.next_slot++ % W.n_slots) : 0u;
     Workspace::Slot& SL = W.slot[slot_id];
     uint64_t budget = static_cast<uint64_t>(s->staging_mib) << 20;
     if (s->staging_mib == 0 && npix64 * ns * 16 <= SL.staging.cap) {
@@ -489,7 +506,15 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
         var = rtiow::pick_plain_smem(s->has_frames, fast, profile, threads);
     }
     if (!var.fn) return set_err(RTIOW_ERR_INVALID_ARG, "no kernel instantiation for this cta_threads");
-    const size_t dyn_smem = smem ? B.bytes : 0;
+    // strips of tiles (KParams): as few tiles per strip as the table's room in shared memory allows
+    uint32_t order_shift = 0;
+    {
+        const size_t room = static_cast<size_t>(smem_cap) - (smem ? (B.bytes + 127u) / 128u * 128u : 0u);
+        const uint32_t max_strips = static_cast<uint32_t>(std::min<size_t>(rtiow::kMaxStrips, std::max<size_t>(room / sizeof(uint32_t), 1)));
+        while (((n_groups + (1u << order_shift) - 1u) >> order_shift) > max_strips) ++order_shift;
+    }
+    const uint32_t n_strips = (n_groups + (1u << order_shift) - 1u) >> order_shift, n_tile_slots = n_strips << order_shift;
+    const size_t dyn_smem = (smem ? (B.bytes + 127u) / 128u * 128u : 0u) + static_cast<size_t>(n_strips) * sizeof(uint32_t);
     int num_regs = 0;
     CK(kernel_info(reinterpret_cast<const void*>(var.fn), s->device, s->max_smem_optin, &num_regs));
     int occ = 0;
@@ -516,7 +541,6 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     P.bg_kind = s->bg_kind;
     std::memcpy(P.bg0, s->bg0, 12); std::memcpy(P.bg1, s->bg1, 12);
     P.staging = static_cast<float4*>(SL.staging.p);
-    P.work_counter = SL.d_counter;
     // Scenes whose segments run through a lot of different code (media, wrapper frames, nested subtrees) are
     // bound by instruction fetch: ncu shows `no_instruction` as the top stall with the 99 % hot set at 35 KB against
     // a 32 KB L1.5 I-cache.  Two CTA barriers per round (before hit_top, before shading) keep the 24 warps in the
@@ -535,7 +559,50 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     // Measured (profiles/r01/sweep_v9_refill_threshold.log): book-1 best at 12, Cornell at 4, final at 1.
     P.refill_thr = s->refill_lanes ? s->refill_lanes : (s->costly_segments ? 1u : (s->bg_kind == RTIOW_BG_SKY_GRADIENT ? 12u : 4u));
 
-    P.bottom_first = s->bottom_first ? 1u : 0u;
+    // Tile order.  The kernel ends when the last path ends, and a path of 51 segments takes ~0.15 ms however small the frame
+    // is: per-CTA time stamps (make EXTRA=-DRT_CTA_TIMELINE=1) show the CTAs of an eighth of book-1 living 0.07-0.23 ms
+    // beyond the moment the unit counter runs out, with the paths that started in the last sphere-covered tiles.  So the
+    // fold notes every tile's longest path and sorts the tiles by it (one 6-bit radix pass, stable: ties stay bottom
+    // first), and the slot's NEXT render of the same shape hands the tiles with long paths out first and ends with the
+    // ones that had none.  A hint only: the image does not depend on the order, and a render that has no previous one
+    // (or follows one of another shape) takes its tiles bottom rows first.
+    const uint64_t shape[4] = {(static_cast<uint64_t>(nx) << 32) | ny, (static_cast<uint64_t>(r0) << 32) | r1,
+                               (static_cast<uint64_t>(step) << 32) | band,
+                               (static_cast<uint64_t>(tile_first) << 40) | (static_cast<uint64_t>(tile_step) << 16) | order_shift};
+    const bool want_order = s->order_hint && n_groups >= 1024u && !d_samples && s->bottom_first;
+    P.n_strips = n_strips; P.order_shift = order_shift;
+    const bool have_order = want_order && SL.order_valid && std::equal(shape, shape + 4, SL.order_shape);
+    // learning costs a sort behind the fold, and with the tail gone nothing hides it: an order is kept for 16 renders
+    const bool learn_order = want_order && (!have_order || ++SL.order_age >= 16u);
+    const size_t table_bytes = (rtiow::kOrderHeaderWords + static_cast<size_t>(n_strips)) * sizeof(uint32_t);
+    auto table_of = [](DevBuf& b) { return static_cast<uint32_t*>(b.p) + rtiow::kOrderHeaderWords; };
+    size_t sort_tmp_bytes = 0;
+    if (learn_order)
+        CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_tmp_bytes, static_cast<const uint32_t*>(nullptr),
+                                                      static_cast<uint32_t*>(nullptr), static_cast<const uint32_t*>(nullptr),
+                                                      static_cast<uint32_t*>(nullptr), static_cast<int>(n_strips), 0, 6, stream));
+    bool order_usable = have_order;
+    if (table_bytes > SL.tiles_in.cap || (learn_order && (table_bytes > SL.tile_order.cap || sort_tmp_bytes > SL.sort_tmp.cap))) {
+        CK(cudaStreamSynchronize(SL.stream));  // the buffers are about to be replaced
+        if (SL.fold_recorded) CK(cudaEventSynchronize(SL.fold_done));
+        order_usable = false;
+        SL.order_valid = false;
+        SL.default_order_n = 0;
+    }
+    CK(SL.tiles_in.reserve(table_bytes));
+    if (learn_order) {
+        CK(SL.longest.reserve(table_bytes)); CK(SL.longest_sorted.reserve(table_bytes)); CK(SL.tile_order.reserve(table_bytes));
+        CK(SL.sort_tmp.reserve(std::max<size_t>(sort_tmp_bytes, 16)));
+    }
+    // the default order, bottom tile first (also the sort's values); rewritten only when the number of tiles changes
+    const uint32_t default_tag = n_strips * 2u + (s->bottom_first ? 1u : 0u);
+    if (SL.default_order_n != default_tag) {
+        if (SL.fold_recorded) CK(cudaStreamWaitEvent(SL.stream, SL.fold_done, 0));  // a sort may still be reading the old one
+        rtiow::iota_kernel<<<(n_strips + 255u) / 256u, 256, 0, SL.stream>>>(table_of(SL.tiles_in), n_strips, s->bottom_first ? 0 : 1);
+        CK(cudaGetLastError());
+        SL.default_order_n = default_tag;
+    }
+    P.work_counter = static_cast<unsigned int*>(order_usable ? SL.tile_order.p : SL.tiles_in.p);  // counter, then the order
     // Work units (KParams): chunks of 8 samples of a tile while there is plenty of work — one atomic, one coherent batch
     // of camera rays per 256 samples — and small chunks for the last fifth or so, because the kernel ends when the last
     // warp finishes its last unit.  Sized so that every resident warp gets >= 8 of the small units (one GPU at C2: 8 + 2;
@@ -584,11 +651,11 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
         } else {
             K.n_chunks_tail = (s_count - K.s_tail_begin + K.s_chunk_tail - 1) / K.s_chunk_tail;
         }
-        if (static_cast<uint64_t>(n_groups) * (K.n_chunks + K.n_chunks_tail) >= (1ull << 32)) {  // keep the unit counter in 32 bits
+        if (static_cast<uint64_t>(n_tile_slots) * (K.n_chunks + K.n_chunks_tail) >= (1ull << 32)) {  // keep the unit counter in 32 bits
             K.s_chunk = s_count; K.n_chunks = 1; K.s_tail_begin = s_count; K.n_chunks_tail = 0; K.s_chunk_tail = 1;
         }
-        K.n_big_units = n_groups * K.n_chunks;
-        K.n_units = K.n_big_units + n_groups * K.n_chunks_tail;
+        K.n_big_units = n_tile_slots * K.n_chunks;  // (the tiles beyond n_groups, padding of the last strip, are empty units)
+        K.n_units = K.n_big_units + n_tile_slots * K.n_chunks_tail;
     };
     // The megakernel runs on the slot's own stream, everything that consumes its samples (export, fold, the peers'
     // hand-shake) on the caller's.  Dependencies: a render needs the previous fold of ITS slot (the staging buffer and the
@@ -606,15 +673,35 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
         P.s_count = std::min(s_pass, ns - P.s_begin);
         plan_units(P.s_count, P);
         if (SL.fold_recorded) CK(cudaStreamWaitEvent(SL.stream, SL.fold_done, 0));
-        CK(cudaMemsetAsync(SL.d_counter, 0, sizeof(unsigned int), SL.stream));
+        CK(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), SL.stream));
+        cudaEvent_t tl[4] = {nullptr, nullptr, nullptr, nullptr};
+        if (s->timeline_on && s->timeline.size() < 4096)
+            for (cudaEvent_t& e : tl) {
+                CK(cudaEventCreate(&e));
+                s->timeline.push_back(e);
+            }
         CK(cudaEventRecord(W.events[s->events_used++], SL.stream));
+        if (tl[0]) CK(cudaEventRecord(tl[0], SL.stream));
+#ifdef RT_CTA_TIMELINE
+        {   // diagnostic build: six time stamps per CTA, kept until scene_destroy prints them
+            std::vector<unsigned long long> init(6u * grid);
+            for (uint32_t b = 0; b < grid; ++b) { init[6 * b + 2] = init[6 * b + 4] = ~0ull; }
+            unsigned long long* d = nullptr;
+            CK(cudaMalloc(reinterpret_cast<void**>(&d), init.size() * 8));
+            CK(cudaMemcpy(d, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+            s->cta_timelines.push_back({d, grid});
+            P.cta_times = d;
+        }
+#endif
         var.fn<<<grid, var.threads, dyn_smem, SL.stream>>>(P);
         CK(cudaGetLastError());
         ++launches;
         CK(cudaEventRecord(W.events[s->events_used++], SL.stream));
+        if (tl[1]) CK(cudaEventRecord(tl[1], SL.stream));
         CK(cudaEventRecord(SL.render_done, SL.stream));
         CK(cudaStreamWaitEvent(stream, SL.render_done, 0));
         CK(cudaEventRecord(W.events[s->events_used++], stream));
+        if (tl[2]) CK(cudaEventRecord(tl[2], stream));
         if (d_samples) {
             const uint64_t n = npix64 * P.s_count;
             rtiow::export_samples_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
@@ -631,13 +718,25 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
                 dst.n = 1u;
             }
             dst.map = tile_map;
+            if (learn_order && pass == 0) CK(cudaMemsetAsync(SL.longest.p, 0, static_cast<size_t>(n_strips) * sizeof(uint32_t), stream));
             rtiow::fold_kernel<<<(npix + 255u) / 256u, 256, 0, stream>>>(
                 P.staging, static_cast<float4*>(SL.accum.p), dst, npix, P.s_count, pass == 0, pass + 1 == n_pass,
-                static_cast<float>(ns), W.d_segs);
+                static_cast<float>(ns), W.d_segs, learn_order ? static_cast<uint32_t*>(SL.longest.p) : nullptr, n_strips, order_shift);
             CK(cudaGetLastError());
             ++launches;
+            if (learn_order && pass + 1 == n_pass) {  // the order for this slot's next render (it waits for fold_done)
+                CK(cub::DeviceRadixSort::SortPairsDescending(SL.sort_tmp.p, sort_tmp_bytes, static_cast<const uint32_t*>(SL.longest.p),
+                                                              static_cast<uint32_t*>(SL.longest_sorted.p),
+                                                              static_cast<const uint32_t*>(table_of(SL.tiles_in)),
+                                                              table_of(SL.tile_order), static_cast<int>(n_strips), 0, 6, stream));
+                ++launches;
+                std::copy(shape, shape + 4, SL.order_shape);
+                SL.order_valid = true;
+                SL.order_age = 0;
+            }
         }
         CK(cudaEventRecord(W.events[s->events_used++], stream));
+        if (tl[3]) CK(cudaEventRecord(tl[3], stream));
         CK(cudaEventRecord(SL.fold_done, stream));
         SL.fold_recorded = true;
     }
@@ -735,8 +834,11 @@ int rtiow_b200_scene_create(const rtiow_scene_desc_t* d, int device, rtiow_scene
     if (const char* env = std::getenv("RTIOW_B200_PIPELINE")) s->pipeline = std::atoi(env) != 0;
     if (const char* env = std::getenv("RTIOW_B200_FUSE_PRISMS")) s->fuse_prisms = std::atoi(env) != 0;
     if (const char* env = std::getenv("RTIOW_B200_UNIT_ORDER")) s->bottom_first = std::atoi(env) != 0;
+    if (const char* env = std::getenv("RTIOW_B200_ORDER_HINT")) s->order_hint = std::atoi(env) != 0;
     if (const char* env = std::getenv("RTIOW_B200_PHASE_SYNC")) s->phase_sync = std::max(0, std::atoi(env));
     if (const char* env = std::getenv("RTIOW_B200_PHASE_GROUP")) s->phase_group_env = static_cast<uint32_t>(std::max(1, std::atoi(env)));
+    if (const char* env = std::getenv("RTIOW_B200_TIMELINE")) s->timeline_on = std::atoi(env) != 0;
+    if (const char* env = std::getenv("RTIOW_B200_SLOTS")) s->ws->n_slots = static_cast<uint32_t>(std::min(4, std::max(1, std::atoi(env))));
     if (const char* env = std::getenv("RTIOW_B200_SAMPLE_CHUNK")) s->sample_chunk = static_cast<uint32_t>(std::max(0, std::atoi(env)));
     {   // build + upload the blob of the selected traversal now, so that render calls only launch
         const rtiow::BlobMode mode = s->traversal == RTIOW_TRAVERSAL_REFERENCE_ORDER ? rtiow::kBlobReferenceOrder
@@ -770,6 +872,42 @@ void rtiow_b200_release_cached_memory(void) {
 void rtiow_b200_scene_destroy(rtiow_scene_t* s) {
     if (!s) return;
     cudaSetDevice(s->device);
+#ifdef RT_CTA_TIMELINE
+    {
+        cudaDeviceSynchronize();
+        unsigned long long t00 = 0;
+        size_t li = 0;
+        for (auto& rec : s->cta_timelines) {
+            std::vector<unsigned long long> h(6u * rec.second);
+            cudaMemcpy(h.data(), rec.first, h.size() * 8, cudaMemcpyDeviceToHost);
+            cudaFree(rec.first);
+            unsigned long long k0 = ~0ull;
+            for (uint32_t b = 0; b < rec.second; ++b) k0 = std::min(k0, h[6 * b]);
+            if (!t00) t00 = k0;
+            // per stamp: min / mean / max over the CTAs, in microseconds since the first CTA of this launch started
+            std::fprintf(stderr, "cta-timeline %3zu: launch at %10.1f us;", li++, (k0 - t00) * 1e-3);
+            static const char* names[6] = {"start", "staged", "first-warp-dry", "last-warp-dry", "first-warp-exit", "last-warp-exit"};
+            for (int k = 0; k < 6; ++k) {
+                double mn = 1e30, mx = 0, sum = 0;
+                for (uint32_t b = 0; b < rec.second; ++b) {
+                    const double v = (h[6 * b + k] - k0) * 1e-3;
+                    mn = std::min(mn, v); mx = std::max(mx, v); sum += v;
+                }
+                std::fprintf(stderr, " %s %.1f/%.1f/%.1f", names[k], mn, sum / rec.second, mx);
+            }
+            std::fprintf(stderr, "\n");
+        }
+    }
+#endif
+    if (!s->timeline.empty()) {  // RTIOW_B200_TIMELINE: when each launch ran, in ms since the first one
+        cudaDeviceSynchronize();
+        for (size_t i = 0; i + 4 <= s->timeline.size(); i += 4) {
+            float t[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], s->timeline[0], s->timeline[i + k]);
+            std::fprintf(stderr, "timeline %4zu: render %9.4f .. %9.4f  fold %9.4f .. %9.4f\n", i / 4, t[0], t[1], t[2], t[3]);
+        }
+        for (cudaEvent_t e : s->timeline) cudaEventDestroy(e);
+    }
     ws_release(s->ws);  // synchronises the scene's stream first; the blobs' device memory stays with the workspace
     delete s;
 }

@@ -34,9 +34,10 @@ struct FoldDst {
 __global__ void __launch_bounds__(256) fold_kernel(const float4* __restrict__ staging, float4* __restrict__ accum,
                                                    const __grid_constant__ FoldDst dst, uint32_t npix, uint32_t s_count,
                                                    int first_pass, int last_pass, float ns_f,
-                                                   unsigned long long* __restrict__ seg_total) {
+                                                   unsigned long long* __restrict__ seg_total,
+                                                   uint32_t* __restrict__ strip_longest, uint32_t n_strips, uint32_t order_shift) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    float segs = 0.f;
+    float segs = 0.f, longest = 0.f;
     uint32_t x = 0, r = 0;
     if (p < npix && dst.map.locate(p, x, r)) {
         float4 acc = first_pass ? make_float4(0.f, 0.f, 0.f, 0.f) : accum[p];
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(256) fold_kernel(const float4* __restrict__ st
             acc.y = acc.y + v.y;
             acc.z = acc.z + v.z;
             segs += v.w;
+            longest = fmaxf(longest, v.w);
         }
         if (last_pass) {
             const size_t o = 3u * (static_cast<size_t>(r) * dst.map.nx + x);
@@ -64,6 +66,21 @@ __global__ void __launch_bounds__(256) fold_kernel(const float4* __restrict__ st
     unsigned long long w = static_cast<unsigned long long>(segs);
     for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
     if ((threadIdx.x & 31u) == 0u && w) atomicAdd(seg_total, w);
+    // A warp is one tile (tile-major staging): its longest path goes into the key of its strip (KParams) — zeroed before the
+    // first pass — stored in REVERSE strip order so that the stable sort leaves equal keys bottom strip first.
+    if (strip_longest != nullptr) {
+        uint32_t m = static_cast<uint32_t>(longest);
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31u) == 0u && p < npix && m != 0u) atomicMax(strip_longest + (n_strips - 1u - ((p >> 5) >> order_shift)), m);
+    }
+}
+
+// The default strip order and the values of the strip-order sort: strip n-1, n-2, ..., 0 — the bottom of the row block
+// first: the kernel ends when the last path ends, and in the reference's scenes the cheap pixels (sky, one segment) are
+// at the top, they make the better tail.  (`ascending`: 0, 1, ..., n-1, for A/B timing.)
+__global__ void __launch_bounds__(256) iota_kernel(uint32_t* __restrict__ out, uint32_t n, int ascending) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = ascending ? i : n - 1u - i;
 }
 
 // ------------------------------------------------------------------------------------------------

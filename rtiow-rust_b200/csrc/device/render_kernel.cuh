@@ -64,12 +64,25 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
 
     using Mem = typename std::conditional<kSmem, MemShared, MemGlobal>::type;
     Mem mem;
+#ifdef RT_CTA_TIMELINE
+    unsigned long long* const tl = P.cta_times + 6u * blockIdx.x;  // [start, staged, first/last warp out of units, first/last warp exit]
+    auto now = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    if (threadIdx.x == 0) tl[0] = now();
+#endif
+    // the strip order (KParams) goes behind the scene; the barrier inside stage_scene_tma publishes it
+    const uint32_t order_s = smem_u32(smem_raw) + (kSmem ? ((P.blob_bytes + 127u) & ~127u) : 0u);
+    for (uint32_t i = threadIdx.x; i < P.n_strips; i += kThreads)
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(order_s + 4u * i), "r"(__ldg(P.work_counter + kOrderHeaderWords + i)) : "memory");
     if constexpr (kSmem) {
         stage_scene_tma(smem_raw, P.blob, P.blob_bytes, &mbar);
         mem.base = smem_u32(smem_raw);
     } else {
+        __syncthreads();
         mem.base = P.blob;
     }
+#ifdef RT_CTA_TIMELINE
+    if (threadIdx.x == 0) tl[1] = now();
+#endif
     const SceneT<Mem, kFeat> sc = scene_views<kFeat>(mem, P);
 
     const uint32_t lane = threadIdx.x & 31u;
@@ -119,7 +132,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
                 uint32_t u = 0;
                 if (lane == 0) u = atomicAdd(P.work_counter, 1u);
                 u = __shfl_sync(0xffffffffu, u, 0);
-                if (u >= P.n_units) { exhausted = true; break; }
+                if (u >= P.n_units) {
+                    exhausted = true;
+#ifdef RT_CTA_TIMELINE
+                    if (lane == 0) { const unsigned long long t = now(); atomicMin(tl + 2, t); atomicMax(tl + 3, t); }
+#endif
+                    break;
+                }
                 // unit u = a chunk of samples of tile g (KParams: two chunk sizes).  Tiles are handed out
                 // from the BOTTOM of the row block: the kernel ends when the last warp finishes its last unit, and in the
                 // reference's scenes the cheap pixels (sky, one segment) are at the top — they make the better tail.
@@ -134,7 +153,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
                     pool_s0 = P.s_tail_begin + (v - g * P.n_chunks_tail) * P.s_chunk_tail;
                     s_n = P.s_count - pool_s0 < P.s_chunk_tail ? P.s_count - pool_s0 : P.s_chunk_tail;
                 }
-                if (P.bottom_first != 0u) g = P.n_groups - 1u - g;
+                {   // g-th tile handed out = tile (mask - g % 2^shift) of the (g >> shift)-th strip of the order (KParams)
+                    uint32_t strip;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(strip) : "r"(order_s + 4u * (g >> P.order_shift)));
+                    g = (strip << P.order_shift) | (~g & ((1u << P.order_shift) - 1u));
+                    if (g >= P.n_groups) { pool_next = pool_end = 0u; continue; }  // padding of the last strip
+                }
                 pool_pix0 = g * 32u;
                 const uint32_t tile = g * P.tile_step + P.tile_first, ty = tile / P.tiles_x;
                 pool_xy = ((ty * kTileH) << 16) | ((tile - ty * P.tiles_x) * kTileW);
@@ -198,6 +222,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
             }
         }
     }
+#ifdef RT_CTA_TIMELINE
+    if (lane == 0) { const unsigned long long t = now(); atomicMin(tl + 4, t); atomicMax(tl + 5, t); }
+#endif
 }
 
 }  // namespace rtiow

@@ -195,6 +195,30 @@ def test_determinism_and_seed():
     assert bits_equal(a, R.cast(64, 32, 8, cam, world, seed=7).rgb)          # cast == par_cast
 
 
+def test_learnt_tile_order_does_not_change_a_bit(oracle):
+    """From the second render of a shape on, the tiles are handed out longest paths first (the previous render's fold
+    sorts the strips of tiles; enqueue_render): a scheduling hint only.  Six renders of the same frame on one handle — the
+    first two without an order (one per pipeline slot), the rest with one — then other seeds (an order learnt from
+    another image), a frame cut into several passes, and a frame with more tiles than the order table has strips: every one
+    bit-identical to the oracle."""
+    nx, ny, ns = 403, 301, 6       # 51 x 76 tiles (ragged on both edges), 3876 of them: one tile per strip
+    world, cam = R.build_scene("book1", nx, ny)
+    want = oracle.Scene("book1", nx, ny).render(ns, seed=0xDEADBEEF, nthreads=NT)[0]
+    for i in range(6):
+        assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, want), i
+    for seed in (5, 6, 7):
+        assert bits_equal(R.par_cast(nx, ny, ns, cam, world, seed=seed).rgb, oracle.Scene("book1", nx, ny).render(ns, seed=seed, nthreads=NT)[0]), seed
+    world.set_tuning(staging_mib=4)                       # 403*301*16 B per sample -> 2 samples per pass
+    for i in range(3):
+        assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, want), ("passes", i)
+    assert world.stats()["passes"] == 3
+    nx, ny, ns = 1000, 700, 2      # 125 x 175 = 21875 tiles: strips of 8 tiles, the last one padded
+    world, cam = R.build_scene("kitchen_sink", nx, ny)
+    want = oracle.Scene("kitchen_sink", nx, ny).render(ns, seed=0xDEADBEEF, nthreads=NT)[0]
+    for i in range(4):
+        assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, want), ("strips", i)
+
+
 def test_ragged_and_tiny_images(oracle):
     """Pixel counts that are not multiples of the 32-pixel warp group, single pixels, single samples."""
     for nx, ny, ns in ((1, 1, 1), (1, 1, 33), (33, 1, 3), (5, 7, 2), (31, 3, 1)):
