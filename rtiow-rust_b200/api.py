@@ -190,8 +190,8 @@ def par_cast(nx, ny, ns, camera, world, seed=DEFAULT_SEED, device=0, rows=None):
 
 def par_cast_multi(nx, ny, ns, camera, worlds, seed=DEFAULT_SEED):
     """par_cast over several GPUs from ONE host thread (rtiow_b200_render_multi): `worlds` = the same scene built once per
-    device, in device order 0, 1, ...  Bands of scanlines are dealt round-robin, every GPU's fold stores its rows straight
-    into GPU 0's frame over NVLink, GPU 0 copies the frame out.  Bit-identical to par_cast."""
+    device, in device order 0, 1, ...  The frame's 8x4-pixel tiles are dealt round-robin, every GPU's fold stores its tiles
+    straight into GPU 0's frame over NVLink, GPU 0 copies the frame out.  Bit-identical to par_cast."""
     lib = worlds[0].lib
     handles = (C.c_void_p * len(worlds))(*[w.gpu(i) for i, w in enumerate(worlds)])
     out = np.empty((ny, nx, 3), np.float32)

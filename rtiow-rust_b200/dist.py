@@ -1,26 +1,21 @@
-"""Multi-GPU sharding of par_cast: one process per GPU (torchrun).  Scanlines are independent
-(src/lib.rs:324-332 parallelises exactly there) and the RNG is keyed by global pixel and sample index,
+"""Multi-GPU sharding of par_cast: one process per GPU (torchrun).  Pixels are independent
+(src/lib.rs:324-332 parallelises over scanlines) and the RNG is keyed by global pixel and sample index,
 so the assembled image is bit-identical for every world size.
 
-Two partitions of the rows:
+Two ways to share the frame out and put it together again:
 
-  interleaved (default)  the frame is cut into bands of 4 scanlines (the height of the kernel's 8x4-pixel
-                         work tiles) and rank r renders bands r, r + G, r + 2G, ...  Every GPU gets the same
-                         mix of cheap (sky: one segment) and expensive (ground, spheres) scanlines.  The
-                         ranks' packed row blocks are exchanged with ONE NCCL all-gather and de-interleaved
-                         by a single strided device copy.
-  contiguous             rank r renders rows [r*ny/G, (r+1)*ny/G) straight into its slice of the frame and
-                         the all-gather is in place (BASELINE.json's "scanline block" wording); simpler, but
-                         on the book-1 scene the top ranks finish early.
-
-Two ways to exchange the rows:
-
-  peer stores (default)  the kernel that finishes a pixel (the in-order sample fold) stores it straight into EVERY
-                         rank's frame through NVLink peer pointers, at the row's final position
-                         (rtiow_b200_render_peers): the exchange is fused into the fold, no collective is called
-                         on the data path, only the ranks' 128-byte frame handles are exchanged once at set-up.
-  NCCL                   one all_gather_into_tensor of the packed rows (+ one strided de-interleave copy for the
-                         interleaved partition): BASELINE.json's wording, kept as the cross-check and fallback.
+  peer stores (default)  the frame's 8x4-pixel tiles (the megakernel's work tiles) are dealt round-robin — rank r renders
+                         tiles r, r + G, ... of the whole frame, so every rank's share is spread evenly over the image —
+                         and the kernel that finishes a pixel (the in-order sample fold) stores it straight into EVERY
+                         rank's frame through NVLink peer pointers, at its final position (rtiow_b200_render_peers):
+                         the exchange is fused into the fold, no collective is called on the data path, only the
+                         ranks' 128-byte frame handles are exchanged once at set-up.
+  NCCL                   BASELINE.json's wording, kept as the cross-check and fallback: the rows are partitioned
+                         (RowShard), every rank renders its packed row block, ONE all_gather_into_tensor exchanges the
+                         blocks.  Two partitions: interleaved (default) — bands of 4 scanlines, rank r renders bands
+                         r, r + G, ..., de-interleaved by a single strided device copy after the gather — and
+                         contiguous — rank r renders rows [r*ny/G, (r+1)*ny/G) straight into its slice of the frame,
+                         the all-gather is in place; simpler, but on the book-1 scene the top ranks finish early.
 
 With one rank nothing is exchanged at all.
 """
@@ -184,7 +179,7 @@ class ShardBuffers:
         if self.peer is not None:
             self._frame = None
             self.mine = self.parts = None
-            self.exchange = ("fused into the sample fold: every finished row is stored into every rank's frame through NVLink peer "
+            self.exchange = ("fused into the sample fold: every finished pixel of this rank's tiles is stored into every rank's frame through NVLink peer "
                              "pointers (rtiow_b200_render_peers); no collective on the data path")
             return
         self._frame = torch.empty((ny, nx, 3), dtype=torch.float32, device=device)
