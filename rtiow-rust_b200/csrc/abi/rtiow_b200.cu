@@ -17,6 +17,7 @@
 
 #include "../device/aux_kernels.cuh"
 #include "kernel_table.hpp"
+#include "unit_plan.hpp"
 #include "scene_blob.hpp"
 
 namespace {
@@ -507,13 +508,11 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     }
     if (!var.fn) return set_err(RTIOW_ERR_INVALID_ARG, "no kernel instantiation for this cta_threads");
     // strips of tiles (KParams): as few tiles per strip as the table's room in shared memory allows
-    uint32_t order_shift = 0;
-    {
-        const size_t room = static_cast<size_t>(smem_cap) - (smem ? (B.bytes + 127u) / 128u * 128u : 0u);
-        const uint32_t max_strips = static_cast<uint32_t>(std::min<size_t>(rtiow::kMaxStrips, std::max<size_t>(room / sizeof(uint32_t), 1)));
-        while (((n_groups + (1u << order_shift) - 1u) >> order_shift) > max_strips) ++order_shift;
-    }
-    const uint32_t n_strips = (n_groups + (1u << order_shift) - 1u) >> order_shift, n_tile_slots = n_strips << order_shift;
+    const size_t order_room = static_cast<size_t>(smem_cap) - (smem ? (B.bytes + 127u) / 128u * 128u : 0u);
+    uint32_t order_shift = 0, n_strips = 0;
+    rtiow::plan_strips(n_groups, static_cast<uint32_t>(std::min<size_t>(rtiow::kMaxStrips, std::max<size_t>(order_room / sizeof(uint32_t), 1))),
+                       &order_shift, &n_strips);
+    const uint32_t n_tile_slots = n_strips << order_shift;
     const size_t dyn_smem = (smem ? (B.bytes + 127u) / 128u * 128u : 0u) + static_cast<size_t>(n_strips) * sizeof(uint32_t);
     int num_regs = 0;
     CK(kernel_info(reinterpret_cast<const void*>(var.fn), s->device, s->max_smem_optin, &num_regs));
@@ -610,52 +609,7 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
     // lost 17 % against T(1)/8 there, most of it per-unit overhead and incoherent refills rather than tail.
     const uint64_t resident_warps = static_cast<uint64_t>(grid) * warps_per_cta;
     auto plan_units = [&](uint32_t s_count, KParams& K) {
-        K.n_groups = n_groups;
-        if (s->sample_chunk != 0u) {  // forced single size
-            K.s_chunk = std::min(s->sample_chunk, s_count);
-            K.s_tail_begin = s_count;
-        } else if (s->bg_kind == RTIOW_BG_SKY_GRADIENT) {
-            // open scenes (most units are cheap sky): ONE size — measured on book-1: 10.68 ms against 10.97 ms with a tail
-            // of smaller units; closed scenes (Cornell: every path is long) gain 3 % from the tail instead.  Which size: a
-            // larger unit saves a share of the whole render (coherent camera rays, fewer atomics), its tail costs a fixed
-            // time, so the best size grows with the square root of the work per warp: the largest c of 8, 4, 2, 1 with
-            // 4 c^2 <= (one-sample units per resident warp) hits the measured optimum for the full book-1 frame and for a
-            // half, a quarter and an eighth of it (profiles/r02/p1_unit_size/)
-            const uint64_t units1 = static_cast<uint64_t>(n_groups) * s_count;
-            uint32_t c = 8u;
-            while (c > 1u && 4ull * c * c * resident_warps > units1) c >>= 1;
-            K.s_chunk = std::min(c, s_count);
-            K.s_tail_begin = s_count;
-        } else {
-            // big chunks: the largest of 8, 4, 2, 1 of which every resident warp still gets >= 24 (a unit must stay a
-            // small fraction of a warp's share: with 3 units of 8 per warp, 8 GPUs lost 25 % to the unlucky warps)
-            const uint32_t body = s_count - (s_count + 4u) / 5u;
-            uint32_t big = 8u;
-            while (big > 1u && static_cast<uint64_t>(n_groups) * (body / big) < 24ull * resident_warps) big >>= 1;
-            K.s_chunk = std::min(big, s_count);
-            // the tail: about a fifth of the samples in chunks of at most half that size, >= 8 per warp
-            const uint64_t want_tail_units = 8ull * resident_warps;
-            uint32_t tail = (s_count + 4u) / 5u;
-            uint32_t small = std::max(1u, K.s_chunk / 2u);
-            while (small > 1u && static_cast<uint64_t>(n_groups) * (tail / small) < want_tail_units) small >>= 1;
-            uint32_t big_samples = (s_count - tail) / K.s_chunk * K.s_chunk;  // whole big chunks
-            if (K.s_chunk == 1u) big_samples = s_count;                        // nothing smaller to end with
-            K.s_tail_begin = big_samples;
-            K.s_chunk_tail = small;
-        }
-        K.n_chunks = K.s_tail_begin / std::max(1u, K.s_chunk) + (K.s_tail_begin % std::max(1u, K.s_chunk) ? 1u : 0u);
-        if (K.s_tail_begin == s_count) {
-            K.n_chunks = (s_count + K.s_chunk - 1) / K.s_chunk;
-            K.s_chunk_tail = 1u;
-            K.n_chunks_tail = 0u;
-        } else {
-            K.n_chunks_tail = (s_count - K.s_tail_begin + K.s_chunk_tail - 1) / K.s_chunk_tail;
-        }
-        if (static_cast<uint64_t>(n_tile_slots) * (K.n_chunks + K.n_chunks_tail) >= (1ull << 32)) {  // keep the unit counter in 32 bits
-            K.s_chunk = s_count; K.n_chunks = 1; K.s_tail_begin = s_count; K.n_chunks_tail = 0; K.s_chunk_tail = 1;
-        }
-        K.n_big_units = n_tile_slots * K.n_chunks;  // (the tiles beyond n_groups, padding of the last strip, are empty units)
-        K.n_units = K.n_big_units + n_tile_slots * K.n_chunks_tail;
+        rtiow::plan_units(n_groups, n_tile_slots, s_count, s->sample_chunk, s->bg_kind == RTIOW_BG_SKY_GRADIENT, resident_warps, K);
     };
     // The megakernel runs on the slot's own stream, everything that consumes its samples (export, fold, the peers'
     // hand-shake) on the caller's.  Dependencies: a render needs the previous fold of ITS slot (the staging buffer and the

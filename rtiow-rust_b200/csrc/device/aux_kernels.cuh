@@ -1,7 +1,7 @@
 // The small kernels around the megakernel: the sample fold, the per-sample export used by parity
 // tests, and print_ppm's quantiser.  Included by the ABI translation unit only.
 #pragma once
-#include "rt_math.cuh"
+#include "path_logic.cuh"
 
 namespace rtiow {
 
@@ -15,16 +15,6 @@ namespace rtiow {
 // of the row block — the whole image in a multi-GPU peer render, where every rank folds its own tiles of it.
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxFoldDst = 16;
-struct TileMap {  // KParams' tiling of the row block
-    uint32_t nx, n_rows, tiles_x, tile_first, tile_step;
-    // staging pixel p -> column x and packed row r; false for the pixels of edge tiles that lie outside the block
-    __device__ __forceinline__ bool locate(uint32_t p, uint32_t& x, uint32_t& r) const {
-        const uint32_t tile = (p >> 5) * tile_step + tile_first, ty = tile / tiles_x;
-        x = (tile - ty * tiles_x) * 8u + (p & 7u);
-        r = ty * 4u + ((p >> 3) & 3u);
-        return x < nx && r < n_rows;
-    }
-};
 struct FoldDst {
     float* p[kMaxFoldDst];
     uint32_t n;

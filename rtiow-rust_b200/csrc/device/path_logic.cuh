@@ -72,6 +72,45 @@ struct KParams {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Work units -> tiles -> pixels (the megakernel's refill, the fold's TileMap and tests/kernel_host_harness.cpp share this)
+// ------------------------------------------------------------------------------------------------
+// Unit u = samples [s0, s0 + s_n) of the pass, of the rank-th tile handed out.
+RT_HD void unit_samples(const KParams& P, uint32_t u, uint32_t& rank, uint32_t& s0, uint32_t& s_n) {
+    if (u < P.n_big_units) {
+        rank = u / P.n_chunks;
+        s0 = (u - rank * P.n_chunks) * P.s_chunk;
+        s_n = P.s_tail_begin - s0 < P.s_chunk ? P.s_tail_begin - s0 : P.s_chunk;
+    } else {
+        const uint32_t v = u - P.n_big_units;
+        rank = v / P.n_chunks_tail;
+        s0 = P.s_tail_begin + (v - rank * P.n_chunks_tail) * P.s_chunk_tail;
+        s_n = P.s_count - s0 < P.s_chunk_tail ? P.s_count - s0 : P.s_chunk_tail;
+    }
+}
+// The rank-th tile handed out is tile (mask - rank % 2^shift) of strip `strip` = order[rank >> shift]: inside a strip the
+// tiles go bottom first.  A result >= n_groups is the padding of the last strip.
+RT_HD uint32_t tile_of_rank(const KParams& P, uint32_t rank, uint32_t strip) {
+    return (strip << P.order_shift) | (~rank & ((1u << P.order_shift) - 1u));
+}
+// First packed row << 16 | first column of tile g of the launch (tile g * tile_step + tile_first of the row block).
+RT_HD uint32_t tile_origin(const KParams& P, uint32_t g) {
+    const uint32_t tile = g * P.tile_step + P.tile_first, ty = tile / P.tiles_x;
+    return ((ty * kTileH) << 16) | ((tile - ty * P.tiles_x) * kTileW);
+}
+
+// The same tiling seen from the staging buffer (fold, sample export): staging slot p = 32 * g + pixel of the tile.
+struct TileMap {
+    uint32_t nx, n_rows, tiles_x, tile_first, tile_step;
+    // staging slot p -> column x and packed row r; false for the pixels of edge tiles that lie outside the block
+    RT_HD bool locate(uint32_t p, uint32_t& x, uint32_t& r) const {
+        const uint32_t tile = (p >> 5) * tile_step + tile_first, ty = tile / tiles_x;
+        x = (tile - ty * tiles_x) * kTileW + (p & (kTileW - 1u));
+        r = ty * kTileH + ((p >> kTileWLog2) & (kTileH - 1u));
+        return x < nx && r < n_rows;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
 // Where the scene blob lives.  The per-path code reads it through one of these accessors (byte
 // offsets into the blob), so the same source runs against shared memory (ld.shared with a 32-bit
 // address: no generic-address arithmetic in the traversal loop), global memory (ld.global.nc, for

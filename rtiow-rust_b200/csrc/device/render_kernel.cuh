@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
                 if (need && !fresh && my_rank < avail) {
                     // job = sample-major over the tile: 32 neighbouring pixels of one sample first
                     const uint32_t job = pool_next + my_rank;
-                    const uint32_t x = (pool_xy & 0xffffu) + (job & (kTileW - 1u)), r = (pool_xy >> 16) + ((job >> kTileWLog2) & (kTileH - 1u));
+                    const uint32_t x = (pool_xy & 0xffffu) + (job & (kTileW - 1u)), r = (pool_xy >> 16) + ((job >> kTileWLog2) & (kTileH - 1u));  // = tile_pixel()
                     if (x < P.nx && r < P.n_rows) {  // tiles on the right / bottom edge are partly outside
                         st.samp = P.s_begin + pool_s0 + (job >> 5);
                         st.pix = pool_pix0 + (job & 31u);  // tile-major staging: a tile's 32 pixels of one sample are 512 contiguous bytes
@@ -139,29 +139,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) render_kernel(const __gr
 #endif
                     break;
                 }
-                // unit u = a chunk of samples of tile g (KParams: two chunk sizes).  Tiles are handed out
-                // from the BOTTOM of the row block: the kernel ends when the last warp finishes its last unit, and in the
-                // reference's scenes the cheap pixels (sky, one segment) are at the top — they make the better tail.
+                // unit u = a chunk of samples of the g-th tile handed out (KParams: two chunk sizes, strip order)
                 uint32_t g, s_n;
-                if (u < P.n_big_units) {
-                    g = u / P.n_chunks;
-                    pool_s0 = (u - g * P.n_chunks) * P.s_chunk;
-                    s_n = P.s_tail_begin - pool_s0 < P.s_chunk ? P.s_tail_begin - pool_s0 : P.s_chunk;
-                } else {
-                    const uint32_t v = u - P.n_big_units;
-                    g = v / P.n_chunks_tail;
-                    pool_s0 = P.s_tail_begin + (v - g * P.n_chunks_tail) * P.s_chunk_tail;
-                    s_n = P.s_count - pool_s0 < P.s_chunk_tail ? P.s_count - pool_s0 : P.s_chunk_tail;
-                }
-                {   // g-th tile handed out = tile (mask - g % 2^shift) of the (g >> shift)-th strip of the order (KParams)
+                unit_samples(P, u, g, pool_s0, s_n);
+                {
                     uint32_t strip;
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(strip) : "r"(order_s + 4u * (g >> P.order_shift)));
-                    g = (strip << P.order_shift) | (~g & ((1u << P.order_shift) - 1u));
+                    g = tile_of_rank(P, g, strip);
                     if (g >= P.n_groups) { pool_next = pool_end = 0u; continue; }  // padding of the last strip
                 }
                 pool_pix0 = g * 32u;
-                const uint32_t tile = g * P.tile_step + P.tile_first, ty = tile / P.tiles_x;
-                pool_xy = ((ty * kTileH) << 16) | ((tile - ty * P.tiles_x) * kTileW);
+                pool_xy = tile_origin(P, g);
                 pool_next = 0u;
                 pool_end = 32u * s_n;
             }

@@ -16,7 +16,8 @@ def lib():
     if _lib is None:
         src = os.path.join(_HERE, "kernel_host_harness.cpp")
         deps = [src] + [os.path.join(_HERE, "..", "rtiow-rust_b200", "csrc", d, f) for d, f in
-                        (("device", "path_logic.cuh"), ("device", "rt_math.cuh"), ("abi", "scene_blob.hpp"), ("abi", "accel_build.hpp"))]
+                        (("device", "path_logic.cuh"), ("device", "rt_math.cuh"), ("abi", "scene_blob.hpp"), ("abi", "accel_build.hpp"),
+                         ("abi", "unit_plan.hpp"))]
         if not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps):
             os.makedirs(os.path.dirname(_SO), exist_ok=True)
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fvisibility=hidden", "-Wl,-Bsymbolic",
@@ -25,6 +26,8 @@ def lib():
         _lib.harness_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
                                         C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32]
         _lib.harness_trace_rays.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+        _lib.harness_unit_coverage.argtypes = [C.c_uint32] * 6 + [C.c_int, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.harness_unit_coverage.restype = C.c_long
     return _lib
 
 
@@ -51,3 +54,17 @@ def render(world, camera, nx, ny, ns, seed=0xDEADBEEF, rows=None, want_samples=F
     if rc:
         raise RuntimeError(f"harness_render failed: {rc}")
     return img, smp
+
+
+def unit_coverage(nx, n_rows, s_count, tile_first=0, tile_step=1, forced_chunk=0, open_scene=True, resident_warps=4736, max_strips=4096,
+                  order=None):
+    """Walks every work unit of one launch like the megakernel's refill does, with the host's own plan.  Returns
+    (counts [n_rows, nx, s_count] uint8 = how often each pixel-sample is handed out, staging slots the fold would misplace,
+    plan dict)."""
+    counts = np.zeros((n_rows, nx, s_count), np.uint8)
+    plan = np.zeros(7, np.uint32)
+    o = None if order is None else np.ascontiguousarray(order, np.uint32)
+    bad = lib().harness_unit_coverage(nx, n_rows, tile_first, tile_step, s_count, forced_chunk, int(open_scene), resident_warps, max_strips,
+                                      None if o is None else o.ctypes.data, counts.ctypes.data, plan.ctypes.data)
+    keys = ("n_groups", "n_strips", "order_shift", "s_chunk", "s_chunk_tail", "s_tail_begin", "n_units")
+    return counts, bad, dict(zip(keys, (int(v) for v in plan)))

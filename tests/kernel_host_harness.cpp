@@ -11,6 +11,7 @@
 
 #include "../rtiow-rust_b200/csrc/abi/scene_blob.hpp"
 #include "../rtiow-rust_b200/csrc/device/path_logic.cuh"
+#include "../rtiow-rust_b200/csrc/abi/unit_plan.hpp"
 
 // accel = 1: the re-indexed (SAH, ordered) traversal with conservative inner box tests that the device
 // uses by default; 2: the same tree with the reference's exact box test at every node; 0: the plain
@@ -200,4 +201,58 @@ extern "C" __attribute__((visibility("default"))) int harness_trace_path(const r
         if (shade_and_scatter(sc, P, st, best, best_t, result)) { ++n; break; }
     }
     return static_cast<int>(n);
+}
+
+
+// Walks every work unit of one launch exactly as the megakernel's refill does (unit_samples, tile_of_rank, tile_origin) with
+// the host's own plan (plan_strips, plan_units), and counts how often each (pixel, sample) of the row block is handed out:
+// counts[(r * nx + x) * s_count + s].  `order`: the strip order (a permutation of 0 .. n_strips-1), null = bottom first.
+// Returns the number of staging slots that the fold's TileMap does NOT map back to the pixel the kernel rendered into
+// them, or -1 for bad arguments.  out_plan: {n_groups, n_strips, order_shift, s_chunk, s_chunk_tail, s_tail_begin, n_units}.
+extern "C" __attribute__((visibility("default")))
+long harness_unit_coverage(uint32_t nx, uint32_t n_rows, uint32_t tile_first, uint32_t tile_step, uint32_t s_count,
+                           uint32_t forced_chunk, int open_scene, uint64_t resident_warps, uint32_t max_strips,
+                           const uint32_t* order, uint8_t* counts, uint32_t* out_plan) {
+    using namespace rtiow;
+    if (nx == 0 || n_rows == 0 || tile_step == 0 || s_count == 0 || nx > 65535u || n_rows > 65535u) return -1;
+    KParams P{};
+    P.nx = nx; P.n_rows = n_rows;
+    P.tiles_x = (nx + kTileW - 1u) / kTileW;
+    const uint32_t tiles_all = P.tiles_x * ((n_rows + kTileH - 1u) / kTileH);
+    if (tile_first >= tiles_all) return 0;
+    P.tile_first = tile_first; P.tile_step = tile_step;
+    const uint32_t n_groups = (tiles_all - tile_first + tile_step - 1u) / tile_step;
+    plan_strips(n_groups, max_strips, &P.order_shift, &P.n_strips);
+    P.s_count = s_count;
+    plan_units(n_groups, P.n_strips << P.order_shift, s_count, forced_chunk, open_scene != 0, resident_warps, P);
+    if (out_plan) {
+        const uint32_t v[7] = {n_groups, P.n_strips, P.order_shift, P.s_chunk, P.s_chunk_tail, P.s_tail_begin, P.n_units};
+        std::memcpy(out_plan, v, sizeof(v));
+    }
+    const TileMap map{nx, n_rows, P.tiles_x, tile_first, tile_step};
+    long bad = 0;
+    for (uint32_t u = 0; u < P.n_units; ++u) {
+        uint32_t rank, s0, s_n;
+        unit_samples(P, u, rank, s0, s_n);
+        const uint32_t strip = order ? order[rank >> P.order_shift] : P.n_strips - 1u - (rank >> P.order_shift);
+        const uint32_t g = tile_of_rank(P, rank, strip);
+        if (g >= P.n_groups) continue;  // padding of the last strip
+        const uint32_t xy = tile_origin(P, g);
+        for (uint32_t job = 0; job < 32u * s_n; ++job) {
+            const uint32_t x = (xy & 0xffffu) + (job & (kTileW - 1u)), r = (xy >> 16) + ((job >> kTileWLog2) & (kTileH - 1u));
+            if (!(x < nx && r < n_rows)) continue;
+            uint32_t fx = 0, fr = 0;
+            if (!map.locate(g * 32u + (job & 31u), fx, fr) || fx != x || fr != r) ++bad;
+            uint8_t& c = counts[(static_cast<size_t>(r) * nx + x) * s_count + s0 + (job >> 5)];
+            if (c < 255) ++c;
+        }
+    }
+    // staging slots of edge tiles that lie outside the block must be skipped by the fold as well
+    for (uint32_t p = 0; p < n_groups * 32u; ++p) {
+        uint32_t fx = 0, fr = 0;
+        const uint32_t xy = tile_origin(P, p >> 5);
+        const uint32_t x = (xy & 0xffffu) + (p & (kTileW - 1u)), r = (xy >> 16) + ((p >> kTileWLog2) & (kTileH - 1u));
+        if (map.locate(p, fx, fr) != (x < nx && r < n_rows)) ++bad;
+    }
+    return bad;
 }

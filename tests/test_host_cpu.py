@@ -454,3 +454,36 @@ def test_feature_specialisations_match_the_general_code(oracle):
         for accel in (1, 2, 0):
             got, _ = H.render(world, cam, nx, ny, ns, accel=accel, lean=True)
             assert n_diff(got, want) == 0, (name, accel)
+
+
+@pytest.mark.parametrize("nx,n_rows,s_count,world,open_scene,warps,max_strips,forced", [
+    (1200, 800, 50, 1, True, 4736, 4096, 0),      # C2 on one GPU: 37500 tiles in strips of 16, units of 8 samples
+    (1200, 800, 50, 8, True, 4736, 4096, 0),      # C2 on 8 GPUs: every rank takes every 8th tile, units of 2 samples
+    (403, 301, 7, 3, True, 4736, 4096, 0),        # ragged on both edges, a world size that divides nothing
+    (800, 800, 37, 4, False, 3552, 4096, 0),      # closed scene: two unit sizes (big chunks + a tail of smaller ones)
+    (333, 97, 5, 2, False, 96, 64, 0),            # few warps and a small order table: strips of several tiles, the last one padded
+    (64, 48, 9, 5, True, 4736, 1, 4),             # one strip for everything (no room for a table), forced chunk, ragged last chunk
+])
+def test_work_units_cover_every_pixel_sample_exactly_once(nx, n_rows, s_count, world, open_scene, warps, max_strips, forced):
+    """The multi-GPU partition and the unit scheduling, walked on the CPU with the very functions the megakernel's refill
+    and the fold use (path_logic.cuh unit_samples / tile_of_rank / tile_origin / TileMap) and the host's own plan
+    (unit_plan.hpp): over the ranks of a world, with a shuffled strip order per rank (any order must do: it is a hint),
+    every pixel-sample of the frame is handed out exactly once, and every staging slot folds back to the pixel that was
+    rendered into it."""
+    rng = np.random.default_rng(nx * 131 + world)
+    total = np.zeros((n_rows, nx, s_count), np.uint16)
+    for rank in range(world):
+        _, _, plan = H.unit_coverage(nx, n_rows, 1, rank, world, forced, open_scene, warps, max_strips)
+        order = rng.permutation(plan["n_strips"]).astype(np.uint32)
+        counts, bad, plan = H.unit_coverage(nx, n_rows, s_count, rank, world, forced, open_scene, warps, max_strips, order=order)
+        assert bad == 0, (rank, plan)
+        assert plan["n_strips"] <= max(1, max_strips) and (plan["n_strips"] << plan["order_shift"]) >= plan["n_groups"]
+        assert counts.max() <= 1, (rank, plan)                      # nothing twice within a rank
+        total += counts
+        default, bad, _ = H.unit_coverage(nx, n_rows, s_count, rank, world, forced, open_scene, warps, max_strips)
+        assert bad == 0 and np.array_equal(default, counts)        # the order changes WHEN a tile is rendered, never WHETHER
+    assert total.min() == 1 and total.max() == 1                    # every pixel-sample exactly once over the world
+    # the ranks' shares are spread evenly: tile counts differ by at most one
+    tiles = ((nx + 7) // 8) * ((n_rows + 3) // 4)
+    shares = [H.unit_coverage(nx, n_rows, 1, r, world, forced, open_scene, warps, max_strips)[2]["n_groups"] for r in range(world)]
+    assert sum(shares) == tiles and max(shares) - min(shares) <= 1
