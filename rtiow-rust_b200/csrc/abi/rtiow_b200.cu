@@ -602,11 +602,9 @@ int enqueue_render(rtiow_scene* s, const rtiow_camera_t* cam, uint32_t nx, uint3
         SL.default_order_n = default_tag;
     }
     P.work_counter = static_cast<unsigned int*>(order_usable ? SL.tile_order.p : SL.tiles_in.p);  // counter, then the order
-    // Work units (KParams): chunks of 8 samples of a tile while there is plenty of work — one atomic, one coherent batch
-    // of camera rays per 256 samples — and small chunks for the last fifth or so, because the kernel ends when the last
-    // warp finishes its last unit.  Sized so that every resident warp gets >= 8 of the small units (one GPU at C2: 8 + 2;
-    // an eighth of the frame on each of 8 GPUs: 8 + 1).  Round 1 used ONE size, 1 sample per unit on 8 GPUs: the kernel
-    // lost 17 % against T(1)/8 there, most of it per-unit overhead and incoherent refills rather than tail.
+    // Work units (KParams): chunks of samples of a tile, sized from the work per resident warp (unit_plan.hpp: one size for
+    // open scenes, big chunks and a tail of smaller ones for closed scenes).  Round 1 used ONE size, 1 sample per unit on 8
+    // GPUs, and lost 17 % against T(1)/8 there, most of it per-unit overhead and incoherent refills.
     const uint64_t resident_warps = static_cast<uint64_t>(grid) * warps_per_cta;
     auto plan_units = [&](uint32_t s_count, KParams& K) {
         rtiow::plan_units(n_groups, n_tile_slots, s_count, s->sample_chunk, s->bg_kind == RTIOW_BG_SKY_GRADIENT, resident_warps, K);
