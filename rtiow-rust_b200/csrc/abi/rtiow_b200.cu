@@ -251,7 +251,11 @@ Workspace* ws_acquire(int device, cudaError_t* err) {
             if (g_ws_cache[i]->device == device) {
                 Workspace* w = g_ws_cache[i];
                 g_ws_cache.erase(g_ws_cache.begin() + static_cast<std::ptrdiff_t>(i));
-                for (Workspace::Slot& sl : w->slot) sl.order_valid = false;  // a tile order belongs to the scene that produced it
+                // The learnt tile orders stay with the workspace: a host application that creates a scene per frame renders
+                // frame k+1 in the order frame k taught.  They are only schedules (any permutation renders the same image);
+                // one inherited from a DIFFERENT scene is merely a worse schedule, and lasts one render: the first render of
+                // the new owner learns its own.
+                for (Workspace::Slot& sl : w->slot) sl.order_age = 15u;
                 return w;
             }
     }

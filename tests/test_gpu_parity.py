@@ -212,6 +212,14 @@ def test_learnt_tile_order_does_not_change_a_bit(oracle):
     for i in range(3):
         assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, want), ("passes", i)
     assert world.stats()["passes"] == 3
+    # the orders stay with the workspace: a handle created after this one is destroyed inherits them — here a DIFFERENT
+    # scene of the same frame shape, rendered first in book-1's order, then in its own
+    world.close()
+    world, cam = R.build_scene("kitchen_sink", nx, ny)
+    want = oracle.Scene("kitchen_sink", nx, ny).render(ns, seed=0xDEADBEEF, nthreads=NT)[0]
+    for i in range(3):
+        assert bits_equal(R.par_cast(nx, ny, ns, cam, world).rgb, want), ("inherited", i)
+    world.close()
     nx, ny, ns = 1000, 700, 2      # 125 x 175 = 21875 tiles: strips of 8 tiles, the last one padded
     world, cam = R.build_scene("kitchen_sink", nx, ny)
     want = oracle.Scene("kitchen_sink", nx, ny).render(ns, seed=0xDEADBEEF, nthreads=NT)[0]
