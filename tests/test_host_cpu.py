@@ -487,3 +487,16 @@ def test_work_units_cover_every_pixel_sample_exactly_once(nx, n_rows, s_count, w
     tiles = ((nx + 7) // 8) * ((n_rows + 3) // 4)
     shares = [H.unit_coverage(nx, n_rows, 1, r, world, forced, open_scene, warps, max_strips)[2]["n_groups"] for r in range(world)]
     assert sum(shares) == tiles and max(shares) - min(shares) <= 1
+
+
+def test_unit_size_rule_picks_the_measured_optima():
+    """unit_plan.hpp: open scenes get one unit size, the largest c of 8, 4, 2, 1 with 4 c^2 <= one-sample units per resident
+    warp — the sizes measured best for the whole book-1 frame and a half, a quarter and an eighth of it on 148 x 32 warps
+    (profiles/r02/p1_unit_size/); closed scenes get big chunks plus a tail of smaller ones that covers every sample."""
+    warps = 148 * 32
+    for world, want in ((1, 8), (2, 4), (4, 4), (8, 2)):
+        plan = H.unit_coverage(1200, 800, 50, 0, world, 0, True, warps, 4096)[2]
+        assert plan["s_chunk"] == want and plan["s_tail_begin"] == 50, (world, plan)
+    plan = H.unit_coverage(800, 800, 100, 0, 1, 0, False, 148 * 32, 4096)[2]       # Cornell at 100 spp on the 1024-thread kernel
+    assert plan["s_chunk"] == 8 and plan["s_chunk_tail"] == 4 and plan["s_tail_begin"] == 80, plan
+    assert H.unit_coverage(64, 48, 3, 0, 1, 0, True, warps, 4096)[2]["s_chunk"] == 1     # a tiny frame: single samples
